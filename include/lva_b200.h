@@ -1,0 +1,126 @@
+/* lva_b200.h -- C ABI of the B200 list-Viterbi decoder (liblva_b200.so).
+ *
+ * The reference (shubhamchandak94/nanopore_dna_storage) has no library or FFI boundary for this
+ * path: its decoder is one function inside one executable,
+ *     decode_post_conv_parallel_LVA   viterbi/viterbi_convolutional_code.cpp:126-129, 589-858
+ * configured by file-scope globals that set_conv_params fills in (:57-75, :264-415) and fed by
+ * read_crf_post (:553-575).  This header is the cut a maintainer would bind if that function
+ * were lifted out of `main` (:137-262): every entry point below names the reference code it
+ * replaces.  Plain C types only; caller-owned buffers; int status codes; one handle per GPU;
+ * a handle may be used by one host thread at a time.
+ *
+ * There is no CPU fallback: lva_create fails if no CUDA device is usable.
+ */
+#ifndef LVA_B200_H_
+#define LVA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVA_DEFAULT_DEVIATION 0xFFFFFFFFu /* "--max-deviation" absent: msg_len+mem_conv+1 (VCC:238-242) */
+
+/* status codes (lva_create / per call) */
+enum {
+  LVA_OK = 0,
+  LVA_ERR_MEM_CONV = 1,      /* VCC:290-292 "Invalid mem_conv (allowed: 6, 8, 11, 14)" */
+  LVA_ERR_RATE = 2,          /* VCC:336-338 "Invalid rate parameter ..." */
+  LVA_ERR_ODD_LENGTH = 3,    /* VCC:353-357 "Output length not even. ..." */
+  LVA_ERR_MARKER_LONG = 4,   /* VCC:391-394 */
+  LVA_ERR_MARKER_PERIOD = 5, /* VCC:396-399 */
+  LVA_ERR_MARKER_CHAR = 6,   /* VCC:409-411 */
+  LVA_ERR_TOO_MANY_STATES = 20, /* VCC:595-597 */
+  LVA_ERR_POST_TOO_SMALL = 21,  /* VCC:600-601  per-read status: T < nstate_pos + 1 */
+  LVA_ERR_MSG_TOO_LONG = 22,    /* VCC:604-605 (and msg_len + mem_conv must fit the 256-bit register) */
+  LVA_ERR_LIST_SIZE = 23,       /* list_size 0 or above LVA_MAX_LIST */
+  LVA_ERR_BAD_ARG = 30,
+  LVA_ERR_NO_DEVICE = 40,       /* no usable CUDA device: there is no CPU path */
+  LVA_ERR_CUDA = 41,
+  LVA_ERR_OOM = 42,
+  LVA_ERR_CODE_STRUCTURE = 43   /* generator polynomials violate the one-predecessor-per-base structure */
+};
+
+#define LVA_MAX_LIST 64u
+
+/* The reference CLI's decode parameters (cxxopts block, VCC:138-172) + globals (VCC:57-75). */
+typedef struct lva_params {
+  uint32_t mem_conv;      /* --mem-conv  6 | 8 | 11 | 14 */
+  uint32_t rate;          /* -r          1,2,3,4,5,7 = 1/2,2/3,3/4,4/5,5/6,7/8 */
+  uint32_t msg_len;       /* --msg-len */
+  uint32_t list_size;     /* -l */
+  uint32_t max_deviation; /* --max-deviation, or LVA_DEFAULT_DEVIATION */
+  int32_t rc;             /* --rc */
+  const char *sync_marker;/* --sync-marker ("" or NULL for none) */
+  uint32_t sync_period;   /* --sync-period */
+  int32_t device;         /* CUDA device ordinal */
+  uint32_t max_slots;     /* reads decoded concurrently (0 = choose from free memory) */
+  uint32_t flags;         /* LVA_FLAG_* */
+} lva_params;
+
+#define LVA_FLAG_EXACT_ONLY 1u /* run every state through the exact heap-order merge (validation mode) */
+
+typedef struct lva_handle lva_handle;
+
+/* Replaces set_conv_params (VCC:264-415) + the table builds at the top of
+ * decode_post_conv_parallel_LVA (VCC:607-650).  Returns NULL on failure and writes an LVA_ERR_*
+ * code to *status (may be NULL) and the reference's message text to err (may be NULL). */
+lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t err_len);
+void lva_destroy(lva_handle *h);
+const char *lva_last_error(const lva_handle *h);
+
+/* Replaces read_crf_post + decode_post_conv_parallel_LVA (VCC:553-575, 589-858) for a batch of
+ * reads.  post = concatenated posterior blocks, 40 floats each in the file order
+ * (VCC:560-571: to*8+from for flip targets, 32+from for the flop target); read i owns blocks
+ * [block_offsets[i], block_offsets[i+1]).  Outputs (caller-owned):
+ *   out_bits   [n_reads][list_size][msg_len]  0/1 bytes, list order and bit order of VCC:826-836
+ *   out_scores [n_reads][list_size]           path metric of each entry (reference: LVA_path_t.score)
+ *   out_counts [n_reads]                      entries produced (<= list_size; 0 = empty list)
+ *   out_status [n_reads]                      LVA_OK or LVA_ERR_POST_TOO_SMALL per read
+ * Any of out_scores / out_status may be NULL.  `post` is HOST memory here. */
+int lva_decode_batch(lva_handle *h, const float *post, const uint64_t *block_offsets,
+                     uint32_t n_reads, uint8_t *out_bits, float *out_scores,
+                     uint32_t *out_counts, int32_t *out_status);
+
+/* Same, with `post` already resident in device memory of the handle's GPU (for callers that
+ * produce posteriors on the GPU, and for kernel-only timing).  Offsets/outputs stay on the host. */
+int lva_decode_batch_device(lva_handle *h, const float *post_dev, const uint64_t *block_offsets,
+                            uint32_t n_reads, uint8_t *out_bits, float *out_scores,
+                            uint32_t *out_counts, int32_t *out_status);
+
+/* conv_encode (VCC:450-499): msg = msg_len 0/1 bytes; out gets 2 bits per base.  Host only. */
+int lva_encode(uint32_t mem_conv, uint32_t rate, const uint8_t *msg, uint32_t msg_len,
+               uint8_t *out_bits, uint32_t out_cap, uint32_t *n_out);
+
+/* Geometry a caller may want (nstate_pos of VCC:74; bases per oligo = nstate_pos - 1). */
+uint32_t lva_nstate_pos(const lva_handle *h);
+uint32_t lva_slots(const lva_handle *h);
+
+/* Work in the reference's unit for a read of T blocks. */
+typedef struct lva_work {
+  double state_updates; /* (step, in-band row, reachable conv state, crf state) */
+  double edge_acs;      /* state updates x incoming edges */
+  double state_bytes;   /* algorithmic state traffic: one read + one write of each live list */
+} lva_work;
+int lva_count_work(const lva_handle *h, uint32_t T, lva_work *out);
+
+/* Timing of the most recent decode call, measured with CUDA events on the handle's stream. */
+typedef struct lva_timing {
+  float total_ms;   /* whole call on the device stream (H2D + kernels + D2H) */
+  float kernel_ms;  /* trellis step launches only */
+  float h2d_ms, d2h_ms;
+  uint64_t launches;        /* kernel launches issued */
+  uint64_t step_launches;   /* of which trellis step kernels */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t exact_fallbacks; /* states resolved by the exact heap-order path after a score tie */
+} lva_timing;
+int lva_get_timing(const lva_handle *h, lva_timing *out);
+
+const char *lva_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVA_B200_H_ */

@@ -1,0 +1,66 @@
+// Device-side data model shared by the trellis kernels.
+//
+// State layout in HBM ("tile-transposed"): a parity buffer holds, for every trellis row p
+// (= nstate_pos index of the reference, VCC:74), C/32 tiles of 32 consecutive conv states.
+// Inside a tile the 32 conv states are the FASTEST index:
+//
+//     word(p, c, s, plane, slot) = row[p].off + (c >> 5) * row[p].tile_words
+//                                + ((s * (1 + nw_p) + plane) * LP + slot) * 32 + (c & 31)
+//
+// plane 0 = path metric (fp32 bits), planes 1..nw_p = message history words (the message bits
+// that have already left the conv register, LSW first; the register itself is the state index).
+// A tile is one contiguous chunk, so a CTA stages its 32 predecessor conv states with ONE bulk
+// copy, shared-memory bank == conv state (conflict-free for any slot / plane / crf pattern), and
+// a warp's 4-byte stores land as complete 32-byte sectors.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "code_tables.hpp"
+
+namespace lva {
+
+constexpr int kCodeSlots = 6;
+constexpr int kTileGroups = 32;  // conv states per HBM tile
+
+struct RowDev {
+  unsigned long long off;  // word offset of the row inside a parity buffer
+  uint32_t vmask, vval;    // conv state reachable iff (c & vmask) == vval   (VCC:944-978)
+  uint32_t tile_words;     // 8 * (1 + idwords) * LP * 32
+  uint8_t block, shift, idwords, dropmask;
+};
+
+struct CodeDev {
+  uint32_t mem, nconv, G0, G1, init, fin, rc, nrows, L, LP;
+  uint32_t pad[2];
+  RowDev row[kMaxRows];
+};
+
+struct ReadDev {
+  unsigned long long post_block;  // first posterior block of the read
+  uint32_t T;                     // number of blocks
+  uint32_t band_off;              // offset of its band-start table
+};
+
+struct StepArgs {
+  uint32_t *state;                // [slot][parity][slot_words]
+  unsigned long long slot_words;
+  const float *post;
+  const ReadDev *reads;
+  const uint16_t *band;
+  unsigned long long *counters;   // [0] exact fallbacks
+  uint32_t t, dev2, code_slot;
+  uint32_t row_lo, row_hi;        // rows this launch is responsible for
+};
+
+struct FinalArgs {
+  const uint32_t *state;
+  unsigned long long slot_words;
+  const ReadDev *reads;
+  uint32_t *out;                  // [slot][8][LP][1 + nw_last]
+  uint32_t code_slot, n_slots;
+};
+
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+
+}  // namespace lva

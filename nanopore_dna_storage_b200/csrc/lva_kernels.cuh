@@ -1,0 +1,365 @@
+// Trellis kernels of the B200 list-Viterbi decoder (sm_100a).
+//
+// One launch = one time step t of the reference's outer loop
+// (/root/reference/viterbi/viterbi_convolutional_code.cpp:667-805, "VCC") for a batch of reads:
+// grid = (conv tiles, band rows, read slots).  A CTA owns the 32 predecessor conv states of one
+// tile of row p-1 (staged once, reused by every target they feed) and computes the TG*8 product
+// states of row p that those predecessors reach -- the butterfly of Appendix B in SURVEY.md.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "heap_order.cuh"
+#include "lva_device.cuh"
+
+namespace lva {
+
+__constant__ CodeDev c_code[kCodeSlots];
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// which base does the conv transition  c_src --(in1[,in2])--> c  emit?   (VCC:440-448, 890-926)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t parity32(uint32_t v) { return __popc(v) & 1u; }
+
+__device__ __forceinline__ uint32_t emitted_base(const CodeDev &K, uint32_t blk, uint32_t c_src,
+                                                 uint32_t in_first, uint32_t in_second) {
+  const uint32_t r = K.rc;
+  if (blk == 0) {
+    const uint32_t w = c_src | (in_first << K.mem);
+    return 2u * (parity32(w & K.G0) ^ r) + (parity32(w & K.G1) ^ r);
+  }
+  const uint32_t w1 = c_src | (in_first << K.mem);
+  const uint32_t o0 = parity32(w1 & K.G0) ^ r, o1 = parity32(w1 & K.G1) ^ r;
+  const uint32_t w2 = (w1 >> 1) | (in_second << K.mem);
+  const uint32_t o2 = parity32(w2 & K.G0) ^ r, o3 = parity32(w2 & K.G1) ^ r;
+  if (blk == 1) return r ? 2u * o2 + o1 : 2u * o1 + o2;
+  if (blk == 2) return r ? 2u * o3 + o0 : 2u * o0 + o3;
+  return r ? 2u * o3 + o1 : 2u * o1 + o3;
+}
+
+// Thread geometry of one CTA: which target state it owns and where its predecessors sit.
+struct Target {
+  uint32_t c;        // target conv state
+  int s;             // target crf state 0..7 (0-3 flip, 4-7 flop)
+  int src_g;         // local index (0..TG-1) of the predecessor conv state inside the staged tile, -1 none
+  uint32_t drop;     // message bits leaving the register on this move (already masked)
+  bool valid;        // (c & vmask) == vval
+};
+
+template <int TG>
+__device__ __forceinline__ Target locate_target(const CodeDev &K, const RowDev &R, uint32_t p, uint32_t tile,
+                                                int tid) {
+  Target T;
+  const int role = tid >= TG * 4;
+  const int q = tid - role * TG * 4;
+  const int tg = q >> 2, b = q & 3;
+  T.s = b + 4 * role;
+  const int sh = p == 0 ? 1 : R.shift;
+  const int per = TG >> sh;                 // consecutive targets per run
+  const uint32_t run = tg / per, idx = tg % per;
+  const uint32_t lo = tile * per + idx;
+  T.c = (run << (K.mem - sh)) | lo;
+  T.valid = (T.c & R.vmask) == R.vval;
+  T.src_g = -1;
+  T.drop = 0;
+  if (p > 0) {
+    const uint32_t c_shift = lo << sh;      // == (c << sh) & (nconv-1)
+    const uint32_t in1 = sh == 1 ? run : (run & 1u), in2 = run >> 1;
+    for (uint32_t xy = 0; xy < (1u << sh); xy++) {
+      if (emitted_base(K, R.block, c_shift | xy, in1, in2) == (uint32_t)b) {
+        T.src_g = (int)((idx << sh) | xy);
+        // bits falling off the low end of the predecessor register, oldest first
+        const uint32_t fell = sh == 1 ? xy : (((xy & 1u) << 1) | (xy >> 1));
+        T.drop = fell & R.dropmask;
+      }
+    }
+  }
+  return T;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact list merge: bit-for-bit the reference's heap-driven k-way merge with de-duplication
+// (VCC:743-800) and its L=1 scan (VCC:715-742), ties included.  Used for every state in
+// validation mode and as the fallback of the register fast path whenever two list heads tie.
+//
+//   src   : staged predecessor tile   [crf][plane][slot][TG]      (shared memory)
+//   mine  : this thread's own list    [plane][slot] stride NT     (shared memory; holds the STAY
+//           list of row p on entry, receives the new list on exit)
+//   post  : the 40 transition scores of step t
+// ---------------------------------------------------------------------------------------------
+// View of the lists one target state merges: its own (stay) list, copied to local memory, and
+// the predecessor lists inside the staged tile.
+template <int LP>
+struct MergeLists {
+  const uint32_t *src;   // staged tile base + src_g
+  int list_stride, plane_stride, tg;  // in words
+  int nws, nwd, sh, s;
+  uint32_t drop;
+  float st_sc[LP];
+  uint32_t st_id[LP * kMaxIdWords];
+
+  __device__ __forceinline__ float src_score(int k, int j) const {
+    return __uint_as_float(src[k * list_stride + j * tg]);
+  }
+  __device__ __forceinline__ float score(int k, int j) const { return k == s ? st_sc[j] : src_score(k, j); }
+  // message history (nwd words) the candidate "entry j of list k" would carry at the target
+  __device__ __forceinline__ void history(int k, int j, uint32_t *id) const {
+    if (k == s) {
+      for (int w = 0; w < nwd; w++) id[w] = st_id[j * kMaxIdWords + w];
+    } else {
+      uint32_t prev = 0;
+      for (int w = 0; w < nwd; w++) {
+        uint32_t old = 0;
+        if (w < nws) old = src[k * list_stride + (1 + w) * plane_stride + j * tg];
+        id[w] = (old << sh) | (w == 0 ? drop : (prev >> (32 - sh)));
+        prev = old;
+      }
+    }
+  }
+};
+
+template <int LP>
+__device__ __noinline__ void exact_merge(const uint32_t *src, uint32_t *mine, const float *post, int L,
+                                         int nws, int nwd, int TGv, int NT, int sh, uint32_t drop, int s,
+                                         int src_g) {
+  const float NEG = neg_inf();
+  MergeLists<LP> M;
+  M.src = src + (src_g >= 0 ? src_g : 0);
+  M.plane_stride = LP * TGv;
+  M.list_stride = (1 + nws) * M.plane_stride;
+  M.tg = TGv;
+  M.nws = nws; M.nwd = nwd; M.sh = sh; M.s = s; M.drop = drop;
+  for (int j = 0; j < L; j++) {
+    M.st_sc[j] = __uint_as_float(mine[j * NT]);
+    for (int w = 0; w < nwd; w++) M.st_id[j * kMaxIdWords + w] = mine[((1 + w) * LP + j) * NT];
+  }
+  const int row = s >= 4 ? 4 : s;
+  const float *wrow = post + row * 8;
+  const int k_first = s < 4 ? 0 : s - 4, k_last = s < 4 ? 7 : s - 4;  // predecessor crf range
+
+  if (L == 1) {  // first strict maximum in predecessor order: stay, then source crf ascending
+    float best = NEG;
+    int bk = -1;
+    {
+      const float sc = M.st_sc[0] + wrow[s];
+      if (sc > best) { best = sc; bk = s; }
+    }
+    if (src_g >= 0) {
+      for (int k = k_first; k <= k_last; k++) {
+        if (k == s) continue;
+        const float sc = M.src_score(k, 0) + wrow[k];
+        if (sc > best) { best = sc; bk = k; }
+      }
+    }
+    mine[0] = __float_as_uint(best);
+    if (bk >= 0) {
+      uint32_t id[kMaxIdWords];
+      M.history(bk, 0, id);
+      for (int w = 0; w < nwd; w++) mine[((1 + w) * LP) * NT] = id[w];
+    }
+    return;
+  }
+
+  float hs[8];
+  uint32_t ht[8];
+  HeapRef H{hs, ht};
+  int n = 0;
+  if (M.st_sc[0] != NEG) { hs[n] = M.st_sc[0] + wrow[s]; ht[n] = (uint32_t)(s << 8); n++; }
+  if (src_g >= 0) {
+    for (int k = k_first; k <= k_last; k++) {
+      if (k == s) continue;
+      const float sc = M.src_score(k, 0);
+      if (sc != NEG) { hs[n] = sc + wrow[k]; ht[n] = (uint32_t)(k << 8); n++; }
+    }
+  }
+  heap_make(H, n);
+  int l = 0;
+  while (n > 0 && l < L) {
+    heap_pop(H, n);
+    n--;
+    const float sc = hs[n];
+    const int k = (int)(ht[n] >> 8), j = (int)(ht[n] & 255u);
+    uint32_t id[kMaxIdWords];
+    M.history(k, j, id);
+    bool dup = false;
+    for (int i = 0; i < l && !dup; i++) {
+      bool same = true;
+      for (int w = 0; w < nwd; w++) same = same && (mine[((1 + w) * LP + i) * NT] == id[w]);
+      dup = same;
+    }
+    if (!dup) {
+      mine[l * NT] = __float_as_uint(sc);
+      for (int w = 0; w < nwd; w++) mine[((1 + w) * LP + l) * NT] = id[w];
+      l++;
+    }
+    if (j == L - 1) continue;
+    const float nxt = M.score(k, j + 1);
+    if (nxt != NEG) {
+      hs[n] = nxt + wrow[k];
+      ht[n] = (uint32_t)((k << 8) | (j + 1));
+      n++;
+      heap_push(H, n);
+    }
+  }
+  for (; l < L; l++) mine[l * NT] = __float_as_uint(NEG);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic step kernel: every width (list slots LP, history words) is a run-time value and every
+// state goes through exact_merge.  Validation mode and fallback for shapes without a
+// specialised kernel.
+//   shared memory: [ post 40 f32 | pad ] [ src tile 8*(1+nws)*LP*TG ] [ own lists (1+nwd)*LP*NT ]
+// ---------------------------------------------------------------------------------------------
+template <int LP, int TG>
+__global__ void __launch_bounds__(TG * 8) lva_step_generic(const StepArgs A) {
+  constexpr int NT = TG * 8;
+  extern __shared__ __align__(128) uint32_t smem[];
+  const CodeDev &K = c_code[A.code_slot];
+  const ReadDev rd = A.reads[blockIdx.z];
+  if (A.t >= rd.T) return;
+  const uint32_t a = A.band[rd.band_off + A.t];
+  uint32_t bend = a + A.dev2;
+  if (bend > K.nrows) bend = K.nrows;
+  if (bend > A.row_hi) bend = A.row_hi;  // a launch may be restricted to rows [row_lo, row_hi)
+  const uint32_t p = (a > A.row_lo ? a : A.row_lo) + blockIdx.y;
+  if (p >= bend) return;
+
+  const RowDev R = K.row[p];
+  const int tid = threadIdx.x;
+  const uint32_t tile = blockIdx.x;
+  const Target T = locate_target<TG>(K, R, p, tile, tid);
+  if (!__syncthreads_or(T.valid)) return;
+
+  const int L = (int)K.L;
+  const int nwd = R.idwords;
+  const int nws = p > 0 ? K.row[p - 1].idwords : 0;
+  float *post = reinterpret_cast<float *>(smem);
+  uint32_t *src = smem + 64;
+  uint32_t *own = src + 8 * (1 + nws) * LP * TG;
+
+  uint32_t *prv = A.state + ((unsigned long long)blockIdx.z * 2 + (A.t & 1u)) * A.slot_words;
+  uint32_t *cur = A.state + ((unsigned long long)blockIdx.z * 2 + ((A.t + 1u) & 1u)) * A.slot_words;
+
+  // ---- stage: posterior block, predecessor tile, own (stay) lists ----
+  if (tid < 10) cp_async16(post + tid * 4, A.post + (rd.post_block + A.t) * 40 + tid * 4);
+  if (p > 0) {
+    const RowDev S = K.row[p - 1];
+    const uint32_t first = tile * TG;  // first predecessor conv state of this CTA
+    const uint32_t *g = prv + S.off + (unsigned long long)(first >> 5) * S.tile_words + (first & 31u);
+    const int lines = 8 * (1 + nws) * LP;      // each line: TG consecutive words
+    constexpr int CH = TG / 4;                 // 16-byte chunks per line
+    for (int i = tid; i < lines * CH; i += NT) {
+      const int line = i / CH, ch = i % CH;
+      cp_async16(src + line * TG + ch * 4, g + (unsigned long long)line * 32 + ch * 4);
+    }
+  }
+  const unsigned long long own_base =
+      R.off + (unsigned long long)(T.c >> 5) * R.tile_words + (T.c & 31u) +
+      (unsigned long long)T.s * (1 + nwd) * LP * 32;
+  for (int i = 0; i < (1 + nwd) * LP; i++) cp_async4(own + i * NT + tid, prv + own_base + (unsigned long long)i * 32);
+  cp_async_wait_all();
+  __syncthreads();
+
+  if (!T.valid) return;
+  uint32_t *mine = own + tid;
+  if (p == 0) {  // VCC:706-713: only the stay edge, only slot 0
+    const int row = T.s >= 4 ? 4 : T.s;
+    mine[0] = __float_as_uint(__uint_as_float(mine[0]) + post[row * 8 + T.s]);
+    for (int l = 1; l < L; l++) mine[l * NT] = __float_as_uint(neg_inf());
+  } else {
+    exact_merge<LP>(src, mine, post, L, nws, nwd, TG, NT, R.shift, T.drop, T.s, T.src_g);
+  }
+  for (int i = 0; i < (1 + nwd) * LP; i++) cur[own_base + (unsigned long long)i * 32] = mine[i * NT];
+}
+
+// ---------------------------------------------------------------------------------------------
+// slot initialisation: every path metric -inf (VCC:611-620), then metric 0 in slot 0 of
+// (row 0, start register, every crf state) of parity buffer 0 (VCC:657-663).
+// ---------------------------------------------------------------------------------------------
+__global__ void lva_fill_neg_inf(uint32_t *state, unsigned long long words) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 4ull;
+  for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 4ull; i < words;
+       i += stride) {
+    *reinterpret_cast<uint4 *>(state + i) = make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u);
+  }
+}
+
+__global__ void lva_seed_start(uint32_t *state, unsigned long long slot_words, uint32_t code_slot,
+                               uint32_t n_slots) {
+  const CodeDev &K = c_code[code_slot];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots * 8) return;
+  const uint32_t slot = i >> 3, s = i & 7;
+  const RowDev R = K.row[0];
+  uint32_t *buf0 = state + (unsigned long long)slot * 2 * slot_words;
+  buf0[R.off + (unsigned long long)(K.init >> 5) * R.tile_words +
+       ((unsigned long long)s * (1 + R.idwords) * K.LP) * 32 + (K.init & 31u)] = 0u;  // 0.0f
+}
+
+// ---------------------------------------------------------------------------------------------
+// final collection (VCC:806-815): the 8*L entries of (last row, end register, every crf state)
+// of the buffer written by the read's last step, as [slot][crf][slot][1+nw] words.
+// ---------------------------------------------------------------------------------------------
+__global__ void lva_collect_final(const FinalArgs A) {
+  const CodeDev &K = c_code[A.code_slot];
+  const uint32_t p = K.nrows - 1;
+  const RowDev R = K.row[p];
+  const uint32_t per_slot = 8 * K.LP;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_slots * per_slot) return;
+  const uint32_t slot = i / per_slot, e = i % per_slot, s = e / K.LP, j = e % K.LP;
+  const ReadDev rd = A.reads[slot];
+  const uint32_t *buf = A.state + ((unsigned long long)slot * 2 + (rd.T & 1u)) * A.slot_words;
+  const unsigned long long base = R.off + (unsigned long long)(K.fin >> 5) * R.tile_words + (K.fin & 31u);
+  const uint32_t planes = 1 + R.idwords;
+  for (uint32_t w = 0; w < planes; w++)
+    A.out[(unsigned long long)i * planes + w] = buf[base + ((unsigned long long)(s * planes + w) * K.LP + j) * 32];
+}
+
+}  // namespace lva

