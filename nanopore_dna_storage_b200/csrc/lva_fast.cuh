@@ -1,134 +1,185 @@
-// Register fast path of the trellis step, specialised on list slots (LP) and on the number of
+// Fast path of the trellis step, specialised on list slots (LP) and on the number of
 // message-history words of the target row (NWD).
 //
-// Same CTA geometry as lva_step_generic with TG = 32 (one HBM tile of predecessors per CTA):
-//   * the predecessor tile is ONE contiguous chunk -> a single TMA bulk copy (cp.async.bulk,
-//     SASS UBLKCP) into shared memory, completion on an mbarrier; the step's 40 transition
-//     scores ride on the same barrier;
-//   * each thread owns one target state (p, c, s): warps are role-homogeneous (4 flip warps,
-//     4 flop warps) and the 32 lanes of a warp read 32 DIFFERENT predecessor conv states, which
-//     in the tile-transposed layout are 32 different banks -> no bank conflicts whatever the
-//     (crf, slot, plane) pattern;
-//   * the new list is built in registers by a k-way merge over the list heads with
-//     de-duplication on the message history; whenever two heads tie exactly for the maximum
-//     the thread re-runs that state through exact_merge(), which reproduces libstdc++'s heap
-//     order (VCC:762-795).  Without a tie the pop sequence of any correct k-way merge equals
-//     the reference's, so the fast path is bit-identical by construction.
+// Geometry: one HBM tile of 32 predecessor conv states per CTA, 128 threads, and a ROLE per CTA
+// (blockIdx.x & 1): role 0 computes the 128 flip targets fed by the tile, role 1 the 128 flop
+// targets.  Flip targets merge 8 lists, flop targets 2, so giving them separate CTAs lets the
+// short ones retire and free their SM slot instead of idling beside the long ones.
+//   * the predecessor tile is ONE contiguous chunk (flop CTAs need only its first half, the
+//     four flip lists) -> a single TMA bulk copy (cp.async.bulk, SASS UBLKCP) into shared
+//     memory, completion on an mbarrier; the step's 40 transition scores ride the same barrier;
+//   * each thread owns one target state (p, c, s); the 32 lanes of a warp read 32 DIFFERENT
+//     predecessor conv states, which in the tile-transposed layout are 32 different banks ->
+//     no bank conflicts whatever the (crf, slot, plane) pattern;
+//   * the new list is built by a flat k-way merge (one candidate popped per trip by every lane)
+//     with de-duplication on the message history: a one-word XOR signature per accepted entry
+//     is kept in registers, signature matches are verified word by word in shared memory;
+//   * whenever two list heads tie exactly for the maximum the thread re-runs that state through
+//     exact_merge(), which reproduces libstdc++'s heap order (VCC:762-795).  Without a tie the
+//     pop sequence of any correct k-way merge equals the reference's, so the fast path is
+//     bit-identical by construction.
 #pragma once
 #include "lva_kernels.cuh"
 
 namespace lva {
 
-template <int LP, int NWD>
-struct OutList {
-  float sc[LP];
-  uint32_t id[LP][NWD > 0 ? NWD : 1];
-};
+constexpr int kFastThreads = 128;
 
-// k-way merge of NL lists into `out`.
+// Everything a thread needs to address the lists it merges.
 //   NL = 8 (flip target s < 4): list i is predecessor crf i, except list s which is the state's
 //                               own (stay) list; all weights come from posterior row s.
 //   NL = 2 (flop target s >= 4): list 0 = own list (column s of row 4), list 1 = the flip state
 //                               s-4 of the predecessor conv state (column s-4 of row 4).
-// Returns false if two heads tie exactly for the maximum (caller falls back to exact_merge).
 template <int LP, int NWD, int NL>
-__device__ __forceinline__ bool merge_lists(OutList<LP, NWD> &out, const uint32_t *srcg, const uint32_t *mine,
-                                            const float *wrow, int L, int nws, int sh, uint32_t drop, int s,
-                                            bool has_src) {
-  constexpr int NT = 256, TGc = 32;
-  const float NEG = neg_inf();
-  const int plane_s = LP * TGc, list_s = (1 + nws) * plane_s;
-  const int stay_i = NL == 8 ? s : 0;
-#define LVA_CRF_OF(i) (NL == 8 ? (i) : ((i) == 0 ? s : s - 4))
+struct ListView {
+  static constexpr int NT = kFastThreads, TGc = 32;
+  const uint32_t *srcg, *mine;
+  const float *wrow;
+  int list_s, nws, sh, s;
+  uint32_t drop;
 
+  __device__ __forceinline__ int crf_of(int i) const { return NL == 8 ? i : (i == 0 ? s : s - 4); }
+  __device__ __forceinline__ bool is_stay(int i) const { return NL == 8 ? i == s : i == 0; }
+  __device__ __forceinline__ const uint32_t *base(int i) const {
+    return is_stay(i) ? mine : srcg + crf_of(i) * list_s;
+  }
+  __device__ __forceinline__ int slot_stride(int i) const { return is_stay(i) ? NT : TGc; }
+  __device__ __forceinline__ float score(int i, int j) const {
+    return __uint_as_float(base(i)[j * slot_stride(i)]) + wrow[crf_of(i)];
+  }
+  // message history entry j of list i would carry at the target (NWD words)
+  __device__ __forceinline__ void history(int i, int j, uint32_t (&cand)[NWD > 0 ? NWD : 1]) const {
+    if (NWD == 0) return;
+    const bool st = is_stay(i);
+    const uint32_t *b = base(i);
+    const int ss = st ? NT : TGc, ps = st ? LP * NT : LP * TGc;
+    const int sh_e = st ? 0 : sh;
+    const uint32_t drop_e = st ? 0u : drop;
+    const bool top_word = st || nws == NWD;  // does this list carry NWD words already?
+    uint32_t old[NWD > 0 ? NWD : 1];
+#pragma unroll
+    for (int w = 0; w < NWD; w++) {
+      old[w] = 0;
+      if (w < NWD - 1 || top_word) old[w] = b[(1 + w) * ps + j * ss];
+    }
+    cand[0] = (old[0] << sh_e) | drop_e;
+#pragma unroll
+    for (int w = 1; w < NWD; w++) cand[w] = __funnelshift_l(old[w - 1], old[w], sh_e);
+  }
+};
+
+// arg-max over the list heads as a balanced tree (3 levels for 8 lists)
+template <int NL>
+__device__ __forceinline__ void select_head(const float (&h)[NL], float &best, int &idx) {
+  if (NL == 2) {
+    best = fmaxf(h[0], h[1]);
+    idx = h[0] >= h[1] ? 0 : 1;
+  } else {
+    float m[4];
+    int k[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      m[q] = fmaxf(h[2 * q], h[2 * q + 1]);
+      k[q] = h[2 * q] >= h[2 * q + 1] ? 2 * q : 2 * q + 1;
+    }
+    const float m01 = fmaxf(m[0], m[1]), m23 = fmaxf(m[2], m[3]);
+    const int k01 = m[0] >= m[1] ? k[0] : k[1], k23 = m[2] >= m[3] ? k[2] : k[3];
+    best = fmaxf(m01, m23);
+    idx = m01 >= m23 ? k01 : k23;
+  }
+}
+
+// Flat k-way merge with de-duplication (VCC:743-800) into the thread's shared-memory list
+// `outr` ([plane][slot], stride NT).  Each trip handles one popped candidate; the selection of
+// the NEXT candidate (advance the popped list, arg-max over the heads) does not depend on the
+// accept/duplicate decision of the current one, so both chains sit in one loop body and
+// overlap.  Exact ties are detected lazily: two consecutive pops with equal metric from
+// different lists, or a head equal to the last popped metric when the loop ends.
+// Returns the number of accepted entries, or -1 on a tie (caller falls back to exact_merge).
+template <int LP, int NWD, int NL>
+__device__ __forceinline__ int merge_lists(uint32_t *outr, const ListView<LP, NWD, NL> &V, int L, bool has_src) {
+  constexpr int NT = kFastThreads;
+  const float NEG = neg_inf();
   float h[NL];
 #pragma unroll
-  for (int i = 0; i < NL; i++) {
-    float sc = NEG;
-    if (i == stay_i) sc = __uint_as_float(mine[0]);
-    else if (has_src) sc = __uint_as_float(srcg[LVA_CRF_OF(i) * list_s]);
-    h[i] = sc + wrow[LVA_CRF_OF(i)];
-  }
+  for (int i = 0; i < NL; i++) h[i] = (V.is_stay(i) || has_src) ? V.score(i, 0) : NEG;
+  float best;
+  int i;
+  select_head<NL>(h, best, i);
+  if (best == NEG) return 0;
+  uint32_t sig[LP];
+#pragma unroll
+  for (int a = 0; a < LP; a++) sig[a] = 0;
   uint32_t ptrs = 0;  // 4-bit read position per list
-  bool done = false;
+  int l = 0, prev_i = -1;
+  float prev_best = __int_as_float(0x7f800000);  // +inf: never equals a metric
+  bool tie = false;
+  while (true) {
+    const int j = (ptrs >> (4 * i)) & 15;
+    tie = tie || (best == prev_best && i != prev_i);
+    prev_best = best;
+    prev_i = i;
+    // ---- chain A: history and signature of the current candidate ----
+    uint32_t cand[NWD > 0 ? NWD : 1];
+    V.history(i, j, cand);
+    uint32_t csig = 0;
 #pragma unroll
-  for (int l = 0; l < LP; l++) {
-    out.sc[l] = NEG;
-    if (!done && l < L) {
-      bool accepted = false;
-      while (!accepted) {
-        float best = h[0];
+    for (int w = 0; w < NWD; w++) csig ^= cand[w];
+    // ---- chain B: advance the popped list and select the next candidate ----
+    float nh = NEG;
+    if (j + 1 < L) {
+      nh = V.score(i, j + 1);
+      ptrs += 1u << (4 * i);
+    }
 #pragma unroll
-        for (int i = 1; i < NL; i++) best = fmaxf(best, h[i]);
-        if (best == NEG) { done = true; break; }
-        uint32_t mask = 0;
+    for (int i2 = 0; i2 < NL; i2++) h[i2] = (i2 == i) ? nh : h[i2];
+    float nbest;
+    int ni;
+    select_head<NL>(h, nbest, ni);
+    // ---- chain A continued: de-duplicate, accept ----
+    bool dup;
+    if (NWD == 0) {
+      dup = l > 0;
+    } else {
+      uint32_t m = 0;
 #pragma unroll
-        for (int i = 0; i < NL; i++) mask |= (h[i] == best) ? (1u << i) : 0u;
-        if (mask & (mask - 1u)) return false;  // exact tie between two heads
-        const int i = __ffs(mask) - 1;
-        const int j = (ptrs >> (4 * i)) & 15;
-        const bool is_stay = i == stay_i;
-        const int kc = LVA_CRF_OF(i);
-        const uint32_t *base = is_stay ? mine : srcg + kc * list_s;
-        const int slot_s = is_stay ? NT : TGc, pl_s = is_stay ? LP * NT : plane_s;
-        const int sh_e = is_stay ? 0 : sh;
-        const uint32_t drop_e = is_stay ? 0u : drop;
-        const bool top_word = is_stay || nws == NWD;  // does this list carry NWD words already?
-        // candidate history
-        uint32_t cand[NWD > 0 ? NWD : 1];
-        if (NWD > 0) {
-          uint32_t old[NWD > 0 ? NWD : 1];
+      for (int a = 0; a < LP; a++) m |= (sig[a] == csig) ? (1u << a) : 0u;
+      m &= (1u << l) - 1u;
+      if (NWD == 1) {
+        dup = m != 0;
+      } else {
+        dup = false;
+        while (m != 0 && !dup) {
+          const int a = __ffs(m) - 1;
+          m &= m - 1u;
+          uint32_t diff = 0;
 #pragma unroll
-          for (int w = 0; w < NWD; w++) {
-            old[w] = 0;
-            if (w < NWD - 1 || top_word) old[w] = base[(1 + w) * pl_s + j * slot_s];
-          }
-          cand[0] = (old[0] << sh_e) | drop_e;
-#pragma unroll
-          for (int w = 1; w < NWD; w++) cand[w] = __funnelshift_l(old[w - 1], old[w], sh_e);
-        }
-        // advance list i
-        const int jn = j + 1;
-        float nh = NEG;
-        if (jn < L) {
-          nh = __uint_as_float(base[jn * slot_s]) + wrow[kc];
-          ptrs += 1u << (4 * i);
-        }
-#pragma unroll
-        for (int i2 = 0; i2 < NL; i2++) h[i2] = (i2 == i) ? nh : h[i2];
-        // de-duplicate against what is already in the new list (VCC:778-779)
-        bool dup = false;
-        if (NWD == 0) {
-          dup = l > 0;
-        } else {
-#pragma unroll
-          for (int a = 0; a < l; a++) {
-            uint32_t diff = 0;
-#pragma unroll
-            for (int w = 0; w < NWD; w++) diff |= cand[w] ^ out.id[a][w];
-            dup = dup || (diff == 0);
-          }
-        }
-        if (!dup) {
-          out.sc[l] = best;
-#pragma unroll
-          for (int w = 0; w < NWD; w++) out.id[l][w] = cand[w];
-          accepted = true;
-          if (NWD == 0) done = true;  // every further candidate carries the same (empty) history
-        } else if (NWD == 0) {
-          done = true;
-          break;
+          for (int w = 0; w < NWD - 1; w++) diff |= outr[((1 + w) * LP + a) * NT] ^ cand[w];
+          dup = diff == 0;  // signature equal and all but the last word equal => last word equal
         }
       }
     }
+    if (!dup) {
+      outr[l * NT] = __float_as_uint(best);
+#pragma unroll
+      for (int w = 0; w < NWD; w++) outr[((1 + w) * LP + l) * NT] = cand[w];
+#pragma unroll
+      for (int a = 0; a < LP; a++) sig[a] = (a == l) ? csig : sig[a];
+      l++;
+      if (l == L || NWD == 0) break;  // NWD == 0: every further candidate carries the same (empty) history
+    }
+    if (nbest == NEG) break;
+    best = nbest;
+    i = ni;
   }
-#undef LVA_CRF_OF
-  return true;
+#pragma unroll
+  for (int i2 = 0; i2 < NL; i2++) tie = tie || (h[i2] == prev_best);
+  return tie ? -1 : l;
 }
 
 template <int LP, int NWD>
-__global__ void __launch_bounds__(256) lva_step_fast(const StepArgs A) {
-  constexpr int NT = 256, TG = 32;
+__global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) {
+  constexpr int NT = kFastThreads, TG = 32;
   extern __shared__ __align__(128) uint32_t smem[];
   const CodeDev &K = c_code[A.code_slot];
   const ReadDev rd = A.reads[blockIdx.z];
@@ -142,14 +193,17 @@ __global__ void __launch_bounds__(256) lva_step_fast(const StepArgs A) {
 
   const RowDev R = K.row[p];
   const int tid = threadIdx.x;
-  const uint32_t tile = blockIdx.x;
-  const Target T = locate_target<TG>(K, R, p, tile, tid);
+  const int role = blockIdx.x & 1;  // 0: flip targets, 1: flop targets
+  const uint32_t tile = blockIdx.x >> 1;
+  const Target T = locate_target_q<TG>(K, R, p, tile, tid, role);
 
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);          // bytes 0..7
   float *post = reinterpret_cast<float *>(smem + 4);           // bytes 16..175
   uint32_t *src = smem + 64;                                   // byte 256
   const int nws = p > 0 ? K.row[p - 1].idwords : 0;
-  uint32_t *own = src + 8 * (1 + nws) * LP * TG;
+  const int n_src_lists = role ? 4 : 8;                        // flop targets read only the flip lists 0..3
+  uint32_t *own = src + n_src_lists * (1 + nws) * LP * TG;     // stay lists   [plane][slot][tid]
+  uint32_t *outb = own + (1 + NWD) * LP * NT;                  // new lists    [plane][slot][tid]
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
@@ -162,7 +216,7 @@ __global__ void __launch_bounds__(256) lva_step_fast(const StepArgs A) {
 
   // ---- stage ----
   if (tid == 0) {
-    const uint32_t tile_bytes = p > 0 ? 8u * (1 + nws) * LP * TG * 4u : 0u;
+    const uint32_t tile_bytes = p > 0 ? (uint32_t)n_src_lists * (1 + nws) * LP * TG * 4u : 0u;
     mbar_expect_tx(bar, tile_bytes + 160u);
     bulk_g2s(post, A.post + (rd.post_block + A.t) * 40, 160u, bar);
     if (p > 0) {
@@ -181,78 +235,78 @@ __global__ void __launch_bounds__(256) lva_step_fast(const StepArgs A) {
   mbar_wait(bar, 0);
   if (!T.valid) return;
 
-  OutList<LP, NWD> out;
-  bool in_regs = true;
-  if (p == 0) {  // VCC:706-713
-    const int row = T.s >= 4 ? 4 : T.s;
-#pragma unroll
-    for (int l = 0; l < LP; l++) out.sc[l] = neg_inf();
-    out.sc[0] = __uint_as_float(mine[0]) + post[row * 8 + T.s];
-  } else {
-    const int row = T.s >= 4 ? 4 : T.s;
-    const float *wrow = post + row * 8;
-    const uint32_t *srcg = src + (T.src_g >= 0 ? T.src_g : 0);
-    const bool has_src = T.src_g >= 0;
-    bool ok;
-    if (LP == 1) {
-      // VCC:715-742: first strict maximum, own list first then predecessor crf ascending
-      float best = neg_inf();
-      int bk = -1;
-      const float s0 = __uint_as_float(mine[0]) + wrow[T.s];
-      if (s0 > best) { best = s0; bk = T.s; }
-      const int list_s = (1 + nws) * TG;
-      if (has_src) {
-        const int k0 = T.s < 4 ? 0 : T.s - 4, k1 = T.s < 4 ? 7 : T.s - 4;
-        for (int k = k0; k <= k1; k++) {
-          if (k == T.s) continue;
-          const float sc = __uint_as_float(srcg[k * list_s]) + wrow[k];
-          if (sc > best) { best = sc; bk = k; }
-        }
-      }
-      out.sc[0] = best;
-      if (NWD > 0 && bk >= 0) {
-        if (bk == T.s) {
-#pragma unroll
-          for (int w = 0; w < NWD; w++) out.id[0][w] = mine[(1 + w) * NT];
-        } else {
-          uint32_t prev = 0;
-#pragma unroll
-          for (int w = 0; w < NWD; w++) {
-            uint32_t old = 0;
-            if (w < nws) old = srcg[bk * list_s + (1 + w) * TG];
-            out.id[0][w] = (old << R.shift) | (w == 0 ? T.drop : (prev >> (32 - R.shift)));
-            prev = old;
-          }
-        }
-      } else if (NWD > 0) {
-#pragma unroll
-        for (int w = 0; w < NWD; w++) out.id[0][w] = mine[(1 + w) * NT];  // metric -inf: history is don't-care
-      }
-      ok = true;
-    } else if (T.s < 4) {
-      ok = merge_lists<LP, NWD, 8>(out, srcg, mine, wrow, L, nws, R.shift, T.drop, T.s, has_src);
-    } else {
-      ok = merge_lists<LP, NWD, 2>(out, srcg, mine, wrow, L, nws, R.shift, T.drop, T.s, has_src);
-    }
-    if (!ok) {
-      exact_merge<LP>(src, mine, post, L, nws, NWD, TG, NT, R.shift, T.drop, T.s, T.src_g);
-      atomicAdd(A.counters, 1ull);
-      in_regs = false;
-    }
-  }
   uint32_t *dst = cur + own_base;
-  if (in_regs) {
+  const int row = T.s >= 4 ? 4 : T.s;
+  const float *wrow = post + row * 8;
+  if (p == 0) {  // VCC:706-713: stay edge only, slot 0 only
+    dst[0] = __float_as_uint(__uint_as_float(mine[0]) + wrow[T.s]);
 #pragma unroll
-    for (int l = 0; l < LP; l++) {
-      if (l < L) {
-        dst[l * 32] = __float_as_uint(out.sc[l]);
-#pragma unroll
-        for (int w = 0; w < NWD; w++) dst[((1 + w) * LP + l) * 32] = out.id[l][w];
+    for (int l = 1; l < LP; l++)
+      if (l < L) dst[l * 32] = 0xff800000u;
+    return;
+  }
+  const uint32_t *srcg = src + (T.src_g >= 0 ? T.src_g : 0);
+  const bool has_src = T.src_g >= 0;
+  if (LP == 1) {
+    // VCC:715-742: first strict maximum, own list first then predecessor crf ascending
+    float best = neg_inf();
+    int bk = -1;
+    const float s0 = __uint_as_float(mine[0]) + wrow[T.s];
+    if (s0 > best) { best = s0; bk = T.s; }
+    const int list_s = (1 + nws) * TG;
+    if (has_src) {
+      const int k0 = T.s < 4 ? 0 : T.s - 4, k1 = T.s < 4 ? 7 : T.s - 4;
+      for (int k = k0; k <= k1; k++) {
+        if (k == T.s) continue;
+        const float sc = __uint_as_float(srcg[k * list_s]) + wrow[k];
+        if (sc > best) { best = sc; bk = k; }
       }
     }
+    dst[0] = __float_as_uint(best);
+    if (NWD > 0) {
+      if (bk < 0 || bk == T.s) {  // (metric -inf: history is don't-care)
+#pragma unroll
+        for (int w = 0; w < NWD; w++) dst[(1 + w) * 32] = mine[(1 + w) * NT];
+      } else {
+        uint32_t prev = 0;
+#pragma unroll
+        for (int w = 0; w < NWD; w++) {
+          uint32_t old = 0;
+          if (w < nws) old = srcg[bk * list_s + (1 + w) * TG];
+          dst[(1 + w) * 32] = (old << R.shift) | (w == 0 ? T.drop : (prev >> (32 - R.shift)));
+          prev = old;
+        }
+      }
+    }
+    return;
+  }
+  uint32_t *outr = outb + tid;
+  const uint32_t *res = outr;
+  int n_acc;
+  if (role == 0) {
+    ListView<LP, NWD, 8> V{srcg, mine, wrow, (1 + nws) * LP * TG, nws, (int)R.shift, T.s, T.drop};
+    n_acc = merge_lists<LP, NWD, 8>(outr, V, L, has_src);
   } else {
-    for (int l = 0; l < L; l++)
-      for (int w = 0; w < 1 + NWD; w++) dst[(w * LP + l) * 32] = mine[(w * LP + l) * NT];
+    ListView<LP, NWD, 2> V{srcg, mine, wrow, (1 + nws) * LP * TG, nws, (int)R.shift, T.s, T.drop};
+    n_acc = merge_lists<LP, NWD, 2>(outr, V, L, has_src);
+  }
+  if (n_acc < 0) {  // exact score tie between two list heads: libstdc++ heap order decides
+    exact_merge<LP>(src, mine, post, L, nws, NWD, TG, NT, R.shift, T.drop, T.s, T.src_g);
+    atomicAdd(A.counters, 1ull);
+    res = mine;
+    n_acc = L;
+  }
+  // all lanes store the same (plane, slot) together: each warp store is four complete sectors
+#pragma unroll
+  for (int l = 0; l < LP; l++) {
+    if (l < L) {
+      const bool live = l < n_acc;
+      dst[l * 32] = live ? res[l * NT] : 0xff800000u;
+      if (live) {
+#pragma unroll
+        for (int w = 0; w < NWD; w++) dst[((1 + w) * LP + l) * 32] = res[((1 + w) * LP + l) * NT];
+      }
+    }
   }
 }
 
@@ -260,8 +314,8 @@ __global__ void __launch_bounds__(256) lva_step_fast(const StepArgs A) {
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 inline size_t fast_smem_bytes(uint32_t LP, uint32_t nwd) {
-  // worst case: predecessors carry as many words as the target row
-  return 256 + ((size_t)8 * (1 + nwd) * LP * 32 + (size_t)(1 + nwd) * LP * 256) * 4;
+  // flip CTA, predecessors carrying as many words as the target row: tile + own lists + new lists
+  return 256 + ((size_t)8 * (1 + nwd) * LP * 32 + (size_t)2 * (1 + nwd) * LP * kFastThreads) * 4;
 }
 
 #define LVA_FAST_LP_CASES(X) X(1) X(2) X(4) X(8) X(16)
@@ -291,7 +345,7 @@ inline cudaError_t fast_prepare(uint32_t LP, uint32_t nw_last) {
 
 template <int LP, int NWD>
 inline cudaError_t fast_launch_one(cudaStream_t st, dim3 grid, const StepArgs &a) {
-  lva_step_fast<LP, NWD><<<grid, 256, fast_smem_bytes(LP, NWD), st>>>(a);
+  lva_step_fast<LP, NWD><<<grid, kFastThreads, fast_smem_bytes(LP, NWD), st>>>(a);
   return cudaGetLastError();
 }
 
@@ -305,7 +359,7 @@ inline cudaError_t fast_launch_step(uint32_t LP, cudaStream_t st, StepArgs a, co
     while (q < hi && k.idwords[q] == nw) q++;
     a.row_lo = p;
     a.row_hi = q;
-    dim3 grid(k.nconv / 32, q - p, active);
+    dim3 grid(2 * (k.nconv / 32), q - p, active);  // x: (tile, role)
     cudaError_t e = cudaErrorInvalidValue;
 #define Y(lp, nwc) \
   if (LP == lp && nw == nwc) e = fast_launch_one<lp, nwc>(st, grid, a);

@@ -92,12 +92,11 @@ struct Target {
   bool valid;        // (c & vmask) == vval
 };
 
+// q = index among the TG*4 (target group, base) pairs of the tile; role 0 = flip, 1 = flop
 template <int TG>
-__device__ __forceinline__ Target locate_target(const CodeDev &K, const RowDev &R, uint32_t p, uint32_t tile,
-                                                int tid) {
+__device__ __forceinline__ Target locate_target_q(const CodeDev &K, const RowDev &R, uint32_t p, uint32_t tile,
+                                                  int q, int role) {
   Target T;
-  const int role = tid >= TG * 4;
-  const int q = tid - role * TG * 4;
   const int tg = q >> 2, b = q & 3;
   T.s = b + 4 * role;
   const int sh = p == 0 ? 1 : R.shift;
@@ -121,6 +120,13 @@ __device__ __forceinline__ Target locate_target(const CodeDev &K, const RowDev &
     }
   }
   return T;
+}
+
+template <int TG>
+__device__ __forceinline__ Target locate_target(const CodeDev &K, const RowDev &R, uint32_t p, uint32_t tile,
+                                                int tid) {
+  const int role = tid >= TG * 4;
+  return locate_target_q<TG>(K, R, p, tile, tid - role * TG * 4, role);
 }
 
 // ---------------------------------------------------------------------------------------------
