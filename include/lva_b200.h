@@ -94,6 +94,26 @@ int lva_decode_batch_device(lva_handle *h, const float *post_dev, const uint64_t
 int lva_encode(uint32_t mem_conv, uint32_t rate, const uint8_t *msg, uint32_t msg_len,
                uint8_t *out_bits, uint32_t out_cap, uint32_t *n_out);
 
+/* set_conv_params' acceptance test alone (VCC:264-357): LVA_OK or LVA_ERR_MEM_CONV / _RATE / _ODD_LENGTH.
+ * Host only. */
+int lva_check_params(uint32_t mem_conv, uint32_t rate, uint32_t msg_len);
+
+/* The code tables set_conv_params builds (VCC:57-75, 264-386), for callers and parity tests.
+ * Host only.  punc must hold 16 bytes, pos2msg 260 words.  Returns like lva_check_params. */
+typedef struct lva_code_tables {
+  uint32_t G[2], initial_state, final_state, punc_len, nstate_pos;
+  uint8_t punc[16];
+  uint32_t pos2msg[260];   /* st_pos2msg_pos */
+  uint32_t valid_mask[260], valid_value[260]; /* is_valid_state (VCC:944-978) as (c & mask) == value per row */
+  uint8_t history_words[260];                 /* 32-bit message-history words carried per list entry per row */
+} lva_code_tables;
+int lva_get_code_tables(uint32_t mem_conv, uint32_t rate, uint32_t msg_len, int32_t rc,
+                        const char *sync_marker, uint32_t sync_period, lva_code_tables *out);
+
+/* band of VCC:677-679 for step t of a read of nblk blocks: [*start, *end) */
+void lva_band(uint32_t t, uint32_t nblk, uint32_t nstate_pos, uint32_t max_deviation,
+              uint32_t *start, uint32_t *end);
+
 /* Geometry a caller may want (nstate_pos of VCC:74; bases per oligo = nstate_pos - 1). */
 uint32_t lva_nstate_pos(const lva_handle *h);
 uint32_t lva_slots(const lva_handle *h);

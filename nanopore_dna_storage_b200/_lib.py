@@ -14,7 +14,7 @@ LVA_DEFAULT_DEVIATION = 0xFFFFFFFF
 LVA_FLAG_EXACT_ONLY = 1
 
 EXPORTS = ["lva_create", "lva_destroy", "lva_last_error", "lva_decode_batch", "lva_decode_batch_device",
-           "lva_encode", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_version"]
+           "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_version"]
 
 
 class LvaParams(C.Structure):
@@ -22,6 +22,13 @@ class LvaParams(C.Structure):
                 ("list_size", C.c_uint32), ("max_deviation", C.c_uint32), ("rc", C.c_int32),
                 ("sync_marker", C.c_char_p), ("sync_period", C.c_uint32), ("device", C.c_int32),
                 ("max_slots", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class LvaCodeTables(C.Structure):
+    _fields_ = [("G", C.c_uint32 * 2), ("initial_state", C.c_uint32), ("final_state", C.c_uint32),
+                ("punc_len", C.c_uint32), ("nstate_pos", C.c_uint32), ("punc", C.c_uint8 * 16),
+                ("pos2msg", C.c_uint32 * 260), ("valid_mask", C.c_uint32 * 260),
+                ("valid_value", C.c_uint32 * 260), ("history_words", C.c_uint8 * 260)]
 
 
 class LvaWork(C.Structure):
@@ -71,6 +78,13 @@ def lib() -> C.CDLL:
     L.lva_count_work.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(LvaWork)]
     L.lva_get_timing.restype = C.c_int
     L.lva_get_timing.argtypes = [C.c_void_p, C.POINTER(LvaTiming)]
+    L.lva_get_code_tables.restype = C.c_int
+    L.lva_get_code_tables.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_char_p, C.c_uint32,
+                                      C.POINTER(LvaCodeTables)]
+    L.lva_band.restype = None
+    L.lva_band.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)] * 2
+    L.lva_check_params.restype = C.c_int
+    L.lva_check_params.argtypes = [C.c_uint32] * 3
     L.lva_version.restype = C.c_char_p
     _lib = L
     return L

@@ -335,6 +335,38 @@ int lva_get_timing(const lva_handle *h, lva_timing *out) {
   return LVA_OK;
 }
 
+int lva_check_params(uint32_t mem_conv, uint32_t rate, uint32_t msg_len) {
+  CodeSpec k;
+  return build_code_spec(k, mem_conv, rate, msg_len, false, "", 0);
+}
+
+int lva_get_code_tables(uint32_t mem_conv, uint32_t rate, uint32_t msg_len, int32_t rc, const char *sync_marker,
+                        uint32_t sync_period, lva_code_tables *out) {
+  if (!out) return LVA_ERR_BAD_ARG;
+  CodeSpec k;
+  int st = build_code_spec(k, mem_conv, rate, msg_len, rc != 0, sync_marker ? sync_marker : "", sync_period);
+  if (st != kCodeOk) return st;
+  memset(out, 0, sizeof(*out));
+  out->G[0] = k.G[0]; out->G[1] = k.G[1];
+  out->initial_state = k.init; out->final_state = k.fin;
+  out->punc_len = k.punc_len; out->nstate_pos = k.nrows;
+  for (uint32_t i = 0; i < k.punc_len; i++) out->punc[i] = k.punc[i];
+  for (uint32_t p = 0; p < k.nrows; p++) {
+    out->pos2msg[p] = k.bits_at[p];
+    out->valid_mask[p] = k.vmask[p];
+    out->valid_value[p] = k.vval[p];
+    out->history_words[p] = k.idwords[p];
+  }
+  return LVA_OK;
+}
+
+void lva_band(uint32_t t, uint32_t nblk, uint32_t nstate_pos, uint32_t max_deviation, uint32_t *start,
+              uint32_t *end) {
+  const uint32_t a = band_start(t, nblk, nstate_pos, max_deviation);
+  if (start) *start = a;
+  if (end) *end = band_end(a, nstate_pos, max_deviation);
+}
+
 int lva_encode(uint32_t mem_conv, uint32_t rate, const uint8_t *msg, uint32_t msg_len, uint8_t *out_bits,
                uint32_t out_cap, uint32_t *n_out) {
   CodeSpec k;

@@ -123,3 +123,24 @@ def conv_encode(msg_bits, mem_conv: int, rate: int) -> np.ndarray:
     if st != 0:
         raise LvaError(st, "encode failed")
     return out[:n.value].copy()
+
+
+def code_tables(mem_conv: int, rate: int, msg_len: int, rc: bool = False, sync_marker: str = "",
+                sync_period: int = 0) -> dict:
+    """The tables set_conv_params builds (VCC:264-415), plus the per-row validity mask."""
+    L = _lib.lib()
+    t = _lib.LvaCodeTables()
+    st = L.lva_get_code_tables(mem_conv, rate, msg_len, int(rc), sync_marker.encode(), sync_period, C.byref(t))
+    if st != 0:
+        raise LvaError(st, "bad code parameters")
+    P = t.nstate_pos
+    return dict(G=(t.G[0], t.G[1]), init=t.initial_state, final=t.final_state, punc=list(t.punc[:t.punc_len]),
+                nstate_pos=P, pos2msg=list(t.pos2msg[:P]), valid_mask=list(t.valid_mask[:P]),
+                valid_value=list(t.valid_value[:P]), history_words=list(t.history_words[:P]))
+
+
+def band(t: int, nblk: int, nstate_pos: int, max_deviation: int):
+    L = _lib.lib()
+    a, b = C.c_uint32(0), C.c_uint32(0)
+    L.lva_band(t, nblk, nstate_pos, max_deviation, C.byref(a), C.byref(b))
+    return a.value, b.value
