@@ -13,7 +13,10 @@
 //     no bank conflicts whatever the (crf, slot, plane) pattern;
 //   * the new list is built by a flat k-way merge (one candidate popped per trip by every lane)
 //     with de-duplication on the message history: a one-word XOR signature per accepted entry
-//     is kept in registers, signature matches are verified word by word in shared memory;
+//     is kept in registers, signature matches (rare: ~1 per state) are verified word by word;
+//     accepted entries are kept as (list, slot) descriptors and materialised when stored;
+//   * states that no conv transition can produce (two of the four bases of every conv state on
+//     rows entered by a one-bit step) are never touched: they keep their initial -inf;
 //   * whenever two list heads tie exactly for the maximum the thread re-runs that state through
 //     exact_merge(), which reproduces libstdc++'s heap order (VCC:762-795).  Without a tie the
 //     pop sequence of any correct k-way merge equals the reference's, so the fast path is
@@ -68,6 +71,32 @@ struct ListView {
   }
 };
 
+// Accepted entries are remembered as (list, slot) descriptors, 8 bits each; metric and history
+// are re-derived from the staged lists when the new list is emitted (and, rarely, when a
+// signature match has to be verified), so no shared-memory output region is needed.
+template <int LP>
+struct Picks {
+  static_assert(LP <= 16, "descriptor words cover at most 16 slots");
+  uint32_t w0, w1, w2, w3;  // scalars on purpose: an indexed array would be demoted to local memory
+  __device__ __forceinline__ void clear() { w0 = w1 = w2 = w3 = 0; }
+  __device__ __forceinline__ void set(int l, uint32_t d) {
+    const uint32_t v = d << (8 * (l & 3));
+    const int q = l >> 2;
+    w0 |= q == 0 ? v : 0u;
+    if (LP > 4) w1 |= q == 1 ? v : 0u;
+    if (LP > 8) w2 |= q == 2 ? v : 0u;
+    if (LP > 12) w3 |= q == 3 ? v : 0u;
+  }
+  __device__ __forceinline__ uint32_t get(int l) const {
+    const int q = l >> 2;
+    uint32_t v = w0;
+    if (LP > 4) v = q == 1 ? w1 : v;
+    if (LP > 8) v = q == 2 ? w2 : v;
+    if (LP > 12) v = q == 3 ? w3 : v;
+    return (v >> (8 * (l & 3))) & 0xffu;
+  }
+};
+
 // arg-max over the list heads as a balanced tree (3 levels for 8 lists)
 template <int NL>
 __device__ __forceinline__ void select_head(const float (&h)[NL], float &best, int &idx) {
@@ -89,17 +118,17 @@ __device__ __forceinline__ void select_head(const float (&h)[NL], float &best, i
   }
 }
 
-// Flat k-way merge with de-duplication (VCC:743-800) into the thread's shared-memory list
-// `outr` ([plane][slot], stride NT).  Each trip handles one popped candidate; the selection of
+// Flat k-way merge with de-duplication (VCC:743-800); the result is the descriptor list
+// `picks`.  Each trip handles one popped candidate; the selection of
 // the NEXT candidate (advance the popped list, arg-max over the heads) does not depend on the
 // accept/duplicate decision of the current one, so both chains sit in one loop body and
 // overlap.  Exact ties are detected lazily: two consecutive pops with equal metric from
 // different lists, or a head equal to the last popped metric when the loop ends.
 // Returns the number of accepted entries, or -1 on a tie (caller falls back to exact_merge).
 template <int LP, int NWD, int NL>
-__device__ __forceinline__ int merge_lists(uint32_t *outr, const ListView<LP, NWD, NL> &V, int L, bool has_src) {
-  constexpr int NT = kFastThreads;
+__device__ __forceinline__ int merge_lists(Picks<LP> &picks, const ListView<LP, NWD, NL> &V, int L, bool has_src) {
   const float NEG = neg_inf();
+  picks.clear();
   float h[NL];
 #pragma unroll
   for (int i = 0; i < NL; i++) h[i] = (V.is_stay(i) || has_src) ? V.score(i, 0) : NEG;
@@ -152,17 +181,18 @@ __device__ __forceinline__ int merge_lists(uint32_t *outr, const ListView<LP, NW
         while (m != 0 && !dup) {
           const int a = __ffs(m) - 1;
           m &= m - 1u;
+          const uint32_t d = picks.get(a);
+          uint32_t acc[NWD > 0 ? NWD : 1];
+          V.history((int)(d >> 4), (int)(d & 15u), acc);
           uint32_t diff = 0;
 #pragma unroll
-          for (int w = 0; w < NWD - 1; w++) diff |= outr[((1 + w) * LP + a) * NT] ^ cand[w];
+          for (int w = 0; w < NWD - 1; w++) diff |= acc[w] ^ cand[w];
           dup = diff == 0;  // signature equal and all but the last word equal => last word equal
         }
       }
     }
     if (!dup) {
-      outr[l * NT] = __float_as_uint(best);
-#pragma unroll
-      for (int w = 0; w < NWD; w++) outr[((1 + w) * LP + l) * NT] = cand[w];
+      picks.set(l, (uint32_t)((i << 4) | j));
 #pragma unroll
       for (int a = 0; a < LP; a++) sig[a] = (a == l) ? csig : sig[a];
       l++;
@@ -175,6 +205,29 @@ __device__ __forceinline__ int merge_lists(uint32_t *outr, const ListView<LP, NW
 #pragma unroll
   for (int i2 = 0; i2 < NL; i2++) tie = tie || (h[i2] == prev_best);
   return tie ? -1 : l;
+}
+
+// Emit the merged list: re-derive metric and history of every pick and store them.  All lanes
+// store the same (plane, slot) together, so each warp store is complete 32-byte sectors.
+template <int LP, int NWD, int NL>
+__device__ __forceinline__ void emit_lists(uint32_t *dst, const Picks<LP> &picks, int n_acc,
+                                           const ListView<LP, NWD, NL> &V, int L) {
+#pragma unroll
+  for (int l = 0; l < LP; l++) {
+    if (l < L) {
+      if (l < n_acc) {
+        const uint32_t d = picks.get(l);
+        const int i = (int)(d >> 4), j = (int)(d & 15u);
+        dst[l * 32] = __float_as_uint(V.score(i, j));
+        uint32_t cand[NWD > 0 ? NWD : 1];
+        V.history(i, j, cand);
+#pragma unroll
+        for (int w = 0; w < NWD; w++) dst[((1 + w) * LP + l) * 32] = cand[w];
+      } else {
+        dst[l * 32] = 0xff800000u;  // -inf; the history words of a dead slot are never read
+      }
+    }
+  }
 }
 
 template <int LP, int NWD>
@@ -193,17 +246,38 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
 
   const RowDev R = K.row[p];
   const int tid = threadIdx.x;
-  const int role = blockIdx.x & 1;  // 0: flip targets, 1: flop targets
+  const int cta_role = blockIdx.x & 1;
   const uint32_t tile = blockIdx.x >> 1;
-  const Target T = locate_target_q<TG>(K, R, p, tile, tid, role);
+  // Rows entered by a one-bit step (puncturing block 0) can produce only two of the four bases
+  // per conv state: the other two flip states and their flop states have no predecessor, are
+  // never reached and keep the -inf they were initialised with.  For such rows ONE CTA per tile
+  // handles the 64 live flip targets (warps 0-1) and the 64 live flop targets (warps 2-3).
+  const bool one_bit = p > 0 && R.shift == 1;
+  if (one_bit && cta_role == 1) return;
+  Target T;
+  int role;
+  if (!one_bit) {
+    role = cta_role;  // 0: the 128 flip targets of the tile, 1: the 128 flop targets
+    T = locate_target_q<TG>(K, R, p, tile, tid, role);
+  } else {
+    role = tid >> 6;
+    const int u = tid & 63, tg = u >> 1;
+    const uint32_t x = u & 1u, run = tg >> 4, idx = tg & 15u;
+    const uint32_t lo = tile * 16u + idx, c_src = (lo << 1) | x;
+    T.c = (run << (K.mem - 1)) | lo;
+    T.s = (int)emitted_base(K, 0, c_src, run, 0) + 4 * role;
+    T.src_g = (int)((idx << 1) | x);
+    T.drop = x & R.dropmask;
+    T.valid = (T.c & R.vmask) == R.vval;
+  }
 
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);          // bytes 0..7
   float *post = reinterpret_cast<float *>(smem + 4);           // bytes 16..175
   uint32_t *src = smem + 64;                                   // byte 256
   const int nws = p > 0 ? K.row[p - 1].idwords : 0;
-  const int n_src_lists = role ? 4 : 8;                        // flop targets read only the flip lists 0..3
+  // flop-only CTAs read just the flip lists 0..3 = the first half of the tile
+  const int n_src_lists = (!one_bit && role == 1) ? 4 : 8;
   uint32_t *own = src + n_src_lists * (1 + nws) * LP * TG;     // stay lists   [plane][slot][tid]
-  uint32_t *outb = own + (1 + NWD) * LP * NT;                  // new lists    [plane][slot][tid]
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
@@ -280,33 +354,22 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
     }
     return;
   }
-  uint32_t *outr = outb + tid;
-  const uint32_t *res = outr;
+  Picks<LP> picks;
   int n_acc;
   if (role == 0) {
     ListView<LP, NWD, 8> V{srcg, mine, wrow, (1 + nws) * LP * TG, nws, (int)R.shift, T.s, T.drop};
-    n_acc = merge_lists<LP, NWD, 8>(outr, V, L, has_src);
+    n_acc = merge_lists<LP, NWD, 8>(picks, V, L, has_src);
+    if (n_acc >= 0) emit_lists<LP, NWD, 8>(dst, picks, n_acc, V, L);
   } else {
     ListView<LP, NWD, 2> V{srcg, mine, wrow, (1 + nws) * LP * TG, nws, (int)R.shift, T.s, T.drop};
-    n_acc = merge_lists<LP, NWD, 2>(outr, V, L, has_src);
+    n_acc = merge_lists<LP, NWD, 2>(picks, V, L, has_src);
+    if (n_acc >= 0) emit_lists<LP, NWD, 2>(dst, picks, n_acc, V, L);
   }
   if (n_acc < 0) {  // exact score tie between two list heads: libstdc++ heap order decides
     exact_merge<LP>(src, mine, post, L, nws, NWD, TG, NT, R.shift, T.drop, T.s, T.src_g);
     atomicAdd(A.counters, 1ull);
-    res = mine;
-    n_acc = L;
-  }
-  // all lanes store the same (plane, slot) together: each warp store is four complete sectors
-#pragma unroll
-  for (int l = 0; l < LP; l++) {
-    if (l < L) {
-      const bool live = l < n_acc;
-      dst[l * 32] = live ? res[l * NT] : 0xff800000u;
-      if (live) {
-#pragma unroll
-        for (int w = 0; w < NWD; w++) dst[((1 + w) * LP + l) * 32] = res[((1 + w) * LP + l) * NT];
-      }
-    }
+    for (int l = 0; l < L; l++)
+      for (int w = 0; w < 1 + NWD; w++) dst[(w * LP + l) * 32] = mine[(w * LP + l) * NT];
   }
 }
 
@@ -314,8 +377,8 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 inline size_t fast_smem_bytes(uint32_t LP, uint32_t nwd) {
-  // flip CTA, predecessors carrying as many words as the target row: tile + own lists + new lists
-  return 256 + ((size_t)8 * (1 + nwd) * LP * 32 + (size_t)2 * (1 + nwd) * LP * kFastThreads) * 4;
+  // flip CTA, predecessors carrying as many words as the target row: tile + own (stay) lists
+  return 256 + ((size_t)8 * (1 + nwd) * LP * 32 + (size_t)(1 + nwd) * LP * kFastThreads) * 4;
 }
 
 #define LVA_FAST_LP_CASES(X) X(1) X(2) X(4) X(8) X(16)

@@ -211,6 +211,12 @@ struct Final {
   float score;
 };
 
+// optional statistics for kernel design (tests never enable them): pops per state update,
+// split by target kind: [0] flip with predecessors, [1] flip without, [2] flop with, [3] flop without
+bool g_stats_on = false;
+unsigned long long g_pop_hist[4][80];
+unsigned long long g_acc_hist[4][80];
+
 }  // namespace
 
 extern "C" {
@@ -392,7 +398,9 @@ int lvo_decode(const lvo_params *prm, const float *post, uint32_t nblk, uint8_t 
             }
             std::make_heap(heap.begin(), heap.end());
             uint32_t l = 0;
+            uint32_t npop = 0;
             while (!heap.empty() && l < L) {
+              npop++;
               std::pop_heap(heap.begin(), heap.end());
               HeapItem h = heap.back();
               heap.pop_back();
@@ -409,6 +417,13 @@ int lvo_decode(const lvo_params *prm, const float *post, uint32_t nblk, uint8_t 
                                         h.slot + 1, h.src});
                 std::push_heap(heap.begin(), heap.end());
               }
+            }
+            if (g_stats_on) {
+              const int kind = (s >= 4 ? 2 : 0) + (ne > 1 ? 0 : 1);
+#pragma omp atomic
+              g_pop_hist[kind][npop < 79 ? npop : 79]++;
+#pragma omp atomic
+              g_acc_hist[kind][l < 79 ? l : 79]++;
             }
             for (; l < L; l++) cur_s[x * L + l] = NEG;
           }
@@ -438,6 +453,16 @@ int lvo_decode(const lvo_params *prm, const float *post, uint32_t nblk, uint8_t 
     }
   }
   return 0;
+}
+
+void lvo_stats(int on, unsigned long long *pop_hist, unsigned long long *acc_hist) {
+  if (pop_hist) memcpy(pop_hist, g_pop_hist, sizeof g_pop_hist);
+  if (acc_hist) memcpy(acc_hist, g_acc_hist, sizeof g_acc_hist);
+  if (on >= 0) {
+    g_stats_on = on != 0;
+    memset(g_pop_hist, 0, sizeof g_pop_hist);
+    memset(g_acc_hist, 0, sizeof g_acc_hist);
+  }
 }
 
 // --- libstdc++ heap primitives exposed for the device heap-emulation unit test ---------
