@@ -252,6 +252,15 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
     r.vmask = k.vmask[p]; r.vval = k.vval[p];
     r.tile_words = 8u * (1u + k.idwords[p]) * h->LP * 32u;
     r.block = k.block[p]; r.shift = k.shift[p]; r.idwords = k.idwords[p]; r.dropmask = k.dropmask[p];
+    r.inv_lin = 0; r.lin1 = 0; r.pad0 = r.pad1 = 0; r.pad2 = 0;
+    if (p > 0) {  // linear map low predecessor bits -> emitted base (verified bijective by butterfly_structure_ok)
+      const uint32_t b0 = host_emitted_base(k, k.block[p], 0, 0, 0);
+      for (uint32_t xy = 0; xy < (1u << k.shift[p]); xy++) {
+        const uint32_t t = host_emitted_base(k, k.block[p], xy, 0, 0) ^ b0;
+        r.inv_lin |= (uint8_t)(xy << (2 * t));
+        if (xy == 1) r.lin1 = (uint8_t)t;
+      }
+    }
     off += (unsigned long long)(k.nconv / kTileGroups) * r.tile_words;
   }
   h->slot_words = off;

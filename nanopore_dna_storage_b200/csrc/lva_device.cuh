@@ -28,6 +28,11 @@ struct RowDev {
   uint32_t vmask, vval;    // conv state reachable iff (c & vmask) == vval   (VCC:944-978)
   uint32_t tile_words;     // 8 * (1 + idwords) * LP * 32
   uint8_t block, shift, idwords, dropmask;
+  // The base a conv transition emits is XOR-linear in the predecessor's low `shift` bits xy:
+  // base(c', xy) = base(c', 0) ^ lin[xy].  inv_lin packs, for t = 0..3, the xy with lin[xy] == t
+  // (2 bits each; one-bit steps: only t in {0, lin[1]} exist) and lin1 = lin[1] for one-bit steps.
+  uint8_t inv_lin, lin1, pad0, pad1;
+  uint32_t pad2;
 };
 
 struct CodeDev {

@@ -28,34 +28,42 @@ namespace lva {
 
 constexpr int kFastThreads = 128;
 
-// Everything a thread needs to address the lists it merges.
+// Everything a thread needs to address the lists it merges.  Staged lists -- the predecessor
+// tile and the warp's own (stay) lists -- share one shape: [plane][slot] rows of 32 words.
 //   NL = 8 (flip target s < 4): list i is predecessor crf i, except list s which is the state's
 //                               own (stay) list; all weights come from posterior row s.
 //   NL = 2 (flop target s >= 4): list 0 = own list (column s of row 4), list 1 = the flip state
 //                               s-4 of the predecessor conv state (column s-4 of row 4).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float(lds_u32(addr)); }
+
+// All list accesses go through 32-bit shared-window addresses computed once per thread (plain
+// generic pointers made the compiler rebuild the shared window base inside the merge loop).
 template <int LP, int NWD, int NL>
 struct ListView {
-  static constexpr int NT = kFastThreads, TGc = 32;
-  const uint32_t *srcg, *mine;
-  const float *wrow;
-  int list_s, nws, sh, s;
+  static constexpr uint32_t SS = 32 * 4, PS = LP * 32 * 4;  // slot / plane stride in bytes
+  uint32_t srcg, mine, wrow;  // shared addresses: my predecessor column, my own list, my score row
+  uint32_t list_s;            // bytes between the crf lists of the predecessor tile
+  int nws, sh, s;
   uint32_t drop;
 
   __device__ __forceinline__ int crf_of(int i) const { return NL == 8 ? i : (i == 0 ? s : s - 4); }
   __device__ __forceinline__ bool is_stay(int i) const { return NL == 8 ? i == s : i == 0; }
-  __device__ __forceinline__ const uint32_t *base(int i) const {
-    return is_stay(i) ? mine : srcg + crf_of(i) * list_s;
+  __device__ __forceinline__ uint32_t base(int i) const {
+    return is_stay(i) ? mine : srcg + (uint32_t)crf_of(i) * list_s;
   }
-  __device__ __forceinline__ int slot_stride(int i) const { return is_stay(i) ? NT : TGc; }
   __device__ __forceinline__ float score(int i, int j) const {
-    return __uint_as_float(base(i)[j * slot_stride(i)]) + wrow[crf_of(i)];
+    return lds_f32(base(i) + (uint32_t)j * SS) + lds_f32(wrow + 4u * (uint32_t)crf_of(i));
   }
   // message history entry j of list i would carry at the target (NWD words)
   __device__ __forceinline__ void history(int i, int j, uint32_t (&cand)[NWD > 0 ? NWD : 1]) const {
     if (NWD == 0) return;
     const bool st = is_stay(i);
-    const uint32_t *b = base(i);
-    const int ss = st ? NT : TGc, ps = st ? LP * NT : LP * TGc;
+    const uint32_t b = base(i) + (uint32_t)j * SS;
     const int sh_e = st ? 0 : sh;
     const uint32_t drop_e = st ? 0u : drop;
     const bool top_word = st || nws == NWD;  // does this list carry NWD words already?
@@ -63,7 +71,7 @@ struct ListView {
 #pragma unroll
     for (int w = 0; w < NWD; w++) {
       old[w] = 0;
-      if (w < NWD - 1 || top_word) old[w] = b[(1 + w) * ps + j * ss];
+      if (w < NWD - 1 || top_word) old[w] = lds_u32(b + (1 + w) * PS);
     }
     cand[0] = (old[0] << sh_e) | drop_e;
 #pragma unroll
@@ -71,9 +79,8 @@ struct ListView {
   }
 };
 
-// Accepted entries are remembered as (list, slot) descriptors, 8 bits each; metric and history
-// are re-derived from the staged lists when the new list is emitted (and, rarely, when a
-// signature match has to be verified), so no shared-memory output region is needed.
+// Accepted entries are remembered as (list, slot) descriptors, 8 bits each: a signature match is
+// verified by re-deriving the accepted entry's history from the staged lists.
 template <int LP>
 struct Picks {
   static_assert(LP <= 16, "descriptor words cover at most 16 slots");
@@ -94,6 +101,37 @@ struct Picks {
     if (LP > 8) v = q == 2 ? w2 : v;
     if (LP > 12) v = q == 3 ? w3 : v;
     return (v >> (8 * (l & 3))) & 0xffu;
+  }
+};
+
+// One-byte signatures of the accepted entries, four per register.  match() returns a mask with
+// bit (8*(a&3) + (a>>2)) set for every accepted slot a whose signature MAY equal `sig8` (the
+// zero-byte test can flag a byte above a true match; callers verify), restricted to live slots.
+template <int LP>
+struct SigBytes {
+  static constexpr int NR = (LP + 3) / 4;
+  uint32_t r0, r1, r2, r3, live;
+  __device__ __forceinline__ void clear() { r0 = r1 = r2 = r3 = live = 0; }
+  static __device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {
+    return ((x - 0x01010101u) & ~x & 0x80808080u) >> 7;
+  }
+  __device__ __forceinline__ uint32_t match(uint32_t sig8) const {
+    const uint32_t bc = sig8 * 0x01010101u;
+    uint32_t m = zero_bytes(r0 ^ bc);
+    if (NR > 1) m |= zero_bytes(r1 ^ bc) << 1;
+    if (NR > 2) m |= zero_bytes(r2 ^ bc) << 2;
+    if (NR > 3) m |= zero_bytes(r3 ^ bc) << 3;
+    return m & live;
+  }
+  static __device__ __forceinline__ int slot_of_bit(int pos) { return ((pos & 7) << 2) | (pos >> 3); }
+  __device__ __forceinline__ void insert(int l, uint32_t sig8) {
+    const uint32_t v = sig8 << (8 * (l & 3));
+    const int q = l >> 2;
+    r0 |= q == 0 ? v : 0u;
+    if (NR > 1) r1 |= q == 1 ? v : 0u;
+    if (NR > 2) r2 |= q == 2 ? v : 0u;
+    if (NR > 3) r3 |= q == 3 ? v : 0u;
+    live |= 1u << (8 * (l & 3) + q);
   }
 };
 
@@ -118,17 +156,19 @@ __device__ __forceinline__ void select_head(const float (&h)[NL], float &best, i
   }
 }
 
-// Flat k-way merge with de-duplication (VCC:743-800); the result is the descriptor list
-// `picks`.  Each trip handles one popped candidate; the selection of
-// the NEXT candidate (advance the popped list, arg-max over the heads) does not depend on the
-// accept/duplicate decision of the current one, so both chains sit in one loop body and
-// overlap.  Exact ties are detected lazily: two consecutive pops with equal metric from
-// different lists, or a head equal to the last popped metric when the loop ends.
-// Returns the number of accepted entries, or -1 on a tie (caller falls back to exact_merge).
+// Flat k-way merge with de-duplication (VCC:743-800).  Each trip handles one popped candidate;
+// the selection of the NEXT candidate (advance the popped list, arg-max over the heads) does not
+// depend on the accept/duplicate decision of the current one, so both chains sit in one loop
+// body and overlap.  An accepted candidate is stored to the new list in HBM right away: lanes
+// accept in lock step unless one of them met a duplicate (about once per state), so the stores
+// of a warp still land as complete sectors almost always.  Exact ties are detected lazily: two
+// consecutive pops with equal metric from different lists, or a head equal to the last popped
+// metric when the loop ends.
+// Returns the number of accepted entries, or -1 on a tie (caller falls back to exact_merge and
+// overwrites whatever was stored).
 template <int LP, int NWD, int NL>
-__device__ __forceinline__ int merge_lists(Picks<LP> &picks, const ListView<LP, NWD, NL> &V, int L, bool has_src) {
+__device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD, NL> &V, int L, bool has_src) {
   const float NEG = neg_inf();
-  picks.clear();
   float h[NL];
 #pragma unroll
   for (int i = 0; i < NL; i++) h[i] = (V.is_stay(i) || has_src) ? V.score(i, 0) : NEG;
@@ -136,9 +176,10 @@ __device__ __forceinline__ int merge_lists(Picks<LP> &picks, const ListView<LP, 
   int i;
   select_head<NL>(h, best, i);
   if (best == NEG) return 0;
-  uint32_t sig[LP];
-#pragma unroll
-  for (int a = 0; a < LP; a++) sig[a] = 0;
+  Picks<LP> picks;
+  SigBytes<LP> sigs;
+  picks.clear();
+  sigs.clear();
   uint32_t ptrs = 0;  // 4-bit read position per list
   int l = 0, prev_i = -1;
   float prev_best = __int_as_float(0x7f800000);  // +inf: never equals a metric
@@ -154,6 +195,8 @@ __device__ __forceinline__ int merge_lists(Picks<LP> &picks, const ListView<LP, 
     uint32_t csig = 0;
 #pragma unroll
     for (int w = 0; w < NWD; w++) csig ^= cand[w];
+    csig ^= csig >> 16;
+    csig = (csig ^ (csig >> 8)) & 0xffu;
     // ---- chain B: advance the popped list and select the next candidate ----
     float nh = NEG;
     if (j + 1 < L) {
@@ -170,31 +213,27 @@ __device__ __forceinline__ int merge_lists(Picks<LP> &picks, const ListView<LP, 
     if (NWD == 0) {
       dup = l > 0;
     } else {
-      uint32_t m = 0;
+      uint32_t m = sigs.match(csig);
+      dup = false;
+      while (m != 0 && !dup) {
+        const int a = SigBytes<LP>::slot_of_bit(__ffs(m) - 1);
+        m &= m - 1u;
+        const uint32_t d = picks.get(a);
+        uint32_t acc[NWD > 0 ? NWD : 1];
+        V.history((int)(d >> 4), (int)(d & 15u), acc);
+        uint32_t diff = 0;
 #pragma unroll
-      for (int a = 0; a < LP; a++) m |= (sig[a] == csig) ? (1u << a) : 0u;
-      m &= (1u << l) - 1u;
-      if (NWD == 1) {
-        dup = m != 0;
-      } else {
-        dup = false;
-        while (m != 0 && !dup) {
-          const int a = __ffs(m) - 1;
-          m &= m - 1u;
-          const uint32_t d = picks.get(a);
-          uint32_t acc[NWD > 0 ? NWD : 1];
-          V.history((int)(d >> 4), (int)(d & 15u), acc);
-          uint32_t diff = 0;
-#pragma unroll
-          for (int w = 0; w < NWD - 1; w++) diff |= acc[w] ^ cand[w];
-          dup = diff == 0;  // signature equal and all but the last word equal => last word equal
-        }
+        for (int w = 0; w < NWD; w++) diff |= acc[w] ^ cand[w];
+        dup = diff == 0;
       }
     }
     if (!dup) {
-      picks.set(l, (uint32_t)((i << 4) | j));
+      dst[0] = __float_as_uint(best);  // dst walks the slots of the new list
 #pragma unroll
-      for (int a = 0; a < LP; a++) sig[a] = (a == l) ? csig : sig[a];
+      for (int w = 0; w < NWD; w++) dst[(1 + w) * LP * 32] = cand[w];
+      dst += 32;
+      picks.set(l, (uint32_t)((i << 4) | j));
+      sigs.insert(l, csig);
       l++;
       if (l == L || NWD == 0) break;  // NWD == 0: every further candidate carries the same (empty) history
     }
@@ -205,29 +244,6 @@ __device__ __forceinline__ int merge_lists(Picks<LP> &picks, const ListView<LP, 
 #pragma unroll
   for (int i2 = 0; i2 < NL; i2++) tie = tie || (h[i2] == prev_best);
   return tie ? -1 : l;
-}
-
-// Emit the merged list: re-derive metric and history of every pick and store them.  All lanes
-// store the same (plane, slot) together, so each warp store is complete 32-byte sectors.
-template <int LP, int NWD, int NL>
-__device__ __forceinline__ void emit_lists(uint32_t *dst, const Picks<LP> &picks, int n_acc,
-                                           const ListView<LP, NWD, NL> &V, int L) {
-#pragma unroll
-  for (int l = 0; l < LP; l++) {
-    if (l < L) {
-      if (l < n_acc) {
-        const uint32_t d = picks.get(l);
-        const int i = (int)(d >> 4), j = (int)(d & 15u);
-        dst[l * 32] = __float_as_uint(V.score(i, j));
-        uint32_t cand[NWD > 0 ? NWD : 1];
-        V.history(i, j, cand);
-#pragma unroll
-        for (int w = 0; w < NWD; w++) dst[((1 + w) * LP + l) * 32] = cand[w];
-      } else {
-        dst[l * 32] = 0xff800000u;  // -inf; the history words of a dead slot are never read
-      }
-    }
-  }
 }
 
 template <int LP, int NWD>
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   if (p >= bend) return;
 
   const RowDev R = K.row[p];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta_role = blockIdx.x & 1;
   const uint32_t tile = blockIdx.x >> 1;
   // Rows entered by a one-bit step (puncturing block 0) can produce only two of the four bases
@@ -254,35 +270,50 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   // handles the 64 live flip targets (warps 0-1) and the 64 live flop targets (warps 2-3).
   const bool one_bit = p > 0 && R.shift == 1;
   if (one_bit && cta_role == 1) return;
-  Target T;
-  int role;
-  if (!one_bit) {
+  // ---- which target state is mine, and where do its predecessors sit in the tile ----
+  uint32_t c, drop = 0;
+  int s, src_g = -1, role, pos;  // pos: my word inside the warp's 32-word list rows
+  if (p == 0) {
+    role = cta_role;
+    c = ((uint32_t)(tid >> 6) << (K.mem - 1)) | (tile * 16u + ((tid >> 2) & 15u));
+    s = (tid & 3) + 4 * role;
+    pos = lane;
+  } else if (!one_bit) {
     role = cta_role;  // 0: the 128 flip targets of the tile, 1: the 128 flop targets
-    T = locate_target_q<TG>(K, R, p, tile, tid, role);
+    const uint32_t run = warp, idx = lane >> 2, b = lane & 3u;  // a warp = 8 consecutive conv states x 4 bases
+    const uint32_t lo = tile * 8u + idx;
+    c = (run << (K.mem - 2)) | lo;
+    const uint32_t t = b ^ emitted_base(K, R.block, lo << 2, run & 1u, run >> 1);
+    const uint32_t xy = (R.inv_lin >> (2 * t)) & 3u;
+    src_g = (int)((idx << 2) | xy);
+    drop = (((xy & 1u) << 1) | (xy >> 1)) & R.dropmask;  // bits falling off the register, oldest first
+    s = (int)b + 4 * role;
+    pos = (int)(b * 8u + idx);
   } else {
-    role = tid >> 6;
-    const int u = tid & 63, tg = u >> 1;
-    const uint32_t x = u & 1u, run = tg >> 4, idx = tg & 15u;
-    const uint32_t lo = tile * 16u + idx, c_src = (lo << 1) | x;
-    T.c = (run << (K.mem - 1)) | lo;
-    T.s = (int)emitted_base(K, 0, c_src, run, 0) + 4 * role;
-    T.src_g = (int)((idx << 1) | x);
-    T.drop = x & R.dropmask;
-    T.valid = (T.c & R.vmask) == R.vval;
+    role = warp >> 1;
+    const int u = tid & 63;
+    const uint32_t x = u & 1u, tg = u >> 1, run = tg >> 4, idx = tg & 15u;
+    const uint32_t lo = tile * 16u + idx;
+    c = (run << (K.mem - 1)) | lo;
+    s = (int)(emitted_base(K, 0, lo << 1, run, 0) ^ (x ? R.lin1 : 0u)) + 4 * role;
+    src_g = (int)((idx << 1) | x);
+    drop = x & R.dropmask;
+    pos = lane;
   }
+  const bool valid = (c & R.vmask) == R.vval;
 
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);          // bytes 0..7
   float *post = reinterpret_cast<float *>(smem + 4);           // bytes 16..175
   uint32_t *src = smem + 64;                                   // byte 256
   const int nws = p > 0 ? K.row[p - 1].idwords : 0;
   // flop-only CTAs read just the flip lists 0..3 = the first half of the tile
-  const int n_src_lists = (!one_bit && role == 1) ? 4 : 8;
-  uint32_t *own = src + n_src_lists * (1 + nws) * LP * TG;     // stay lists   [plane][slot][tid]
+  const int n_src_lists = (p > 0 && !one_bit && role == 1) ? 4 : 8;
+  uint32_t *own = src + n_src_lists * (1 + nws) * LP * TG;     // stay lists, per warp [plane][slot][32]
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
   }
-  if (!__syncthreads_or(T.valid)) return;
+  if (!__syncthreads_or(valid)) return;
 
   const int L = (int)K.L;
   uint32_t *prv = A.state + ((unsigned long long)blockIdx.z * 2 + (A.t & 1u)) * A.slot_words;
@@ -298,78 +329,93 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
       bulk_g2s(src, prv + S.off + (unsigned long long)tile * S.tile_words, tile_bytes, bar);
     }
   }
-  const unsigned long long own_base = R.off + (unsigned long long)(T.c >> 5) * R.tile_words + (T.c & 31u) +
-                                      (unsigned long long)T.s * (1 + NWD) * LP * 32;
-  uint32_t *mine = own + tid;
-  if (T.valid) {
+  constexpr int ROWS = (1 + NWD) * LP;                         // [plane][slot] rows of one list
+  uint32_t *wown = own + warp * ROWS * 32;
+  const unsigned long long own_base = R.off + (unsigned long long)(c >> 5) * R.tile_words + (c & 31u) +
+                                      (unsigned long long)s * ROWS * 32;
+  if (p > 0 && !one_bit) {
+    // the warp's 8 conv states are consecutive: every (crf, plane, slot) row is 32 contiguous
+    // bytes in HBM -> 16-byte copies, 8 per lane, instead of 32 4-byte ones
+    const uint32_t c0 = ((uint32_t)warp << (K.mem - 2)) | (tile * 8u);
+    const unsigned long long wbase = R.off + (unsigned long long)(c0 >> 5) * R.tile_words + (c0 & 31u);
 #pragma unroll
-    for (int i = 0; i < (1 + NWD) * LP; i++) cp_async4(mine + i * NT, prv + own_base + (unsigned long long)i * 32);
+    for (int k = 0; k < (ROWS * 8 + 31) / 32; k++) {
+      const int q = lane + 32 * k;
+      const int rowi = q >> 3, piece = (q >> 1) & 3, half = q & 1;
+      if (ROWS % 4 == 0 || q < ROWS * 8)
+        cp_async16(wown + rowi * 32 + piece * 8 + half * 4,
+                   prv + wbase + ((unsigned long long)(piece + 4 * role) * ROWS + rowi) * 32 + half * 4);
+    }
+  } else if (valid) {
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) cp_async4(wown + r * 32 + pos, prv + own_base + (unsigned long long)r * 32);
   }
   cp_async_wait_all();
+  __syncwarp();
   mbar_wait(bar, 0);
-  if (!T.valid) return;
+  if (!valid) return;
 
+  const uint32_t *mine = wown + pos;
   uint32_t *dst = cur + own_base;
-  const int row = T.s >= 4 ? 4 : T.s;
+  const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
   if (p == 0) {  // VCC:706-713: stay edge only, slot 0 only
-    dst[0] = __float_as_uint(__uint_as_float(mine[0]) + wrow[T.s]);
+    dst[0] = __float_as_uint(__uint_as_float(mine[0]) + wrow[s]);
 #pragma unroll
     for (int l = 1; l < LP; l++)
       if (l < L) dst[l * 32] = 0xff800000u;
     return;
   }
-  const uint32_t *srcg = src + (T.src_g >= 0 ? T.src_g : 0);
-  const bool has_src = T.src_g >= 0;
+  const uint32_t *srcg = src + src_g;
   if (LP == 1) {
     // VCC:715-742: first strict maximum, own list first then predecessor crf ascending
     float best = neg_inf();
     int bk = -1;
-    const float s0 = __uint_as_float(mine[0]) + wrow[T.s];
-    if (s0 > best) { best = s0; bk = T.s; }
+    const float s0 = __uint_as_float(mine[0]) + wrow[s];
+    if (s0 > best) { best = s0; bk = s; }
     const int list_s = (1 + nws) * TG;
-    if (has_src) {
-      const int k0 = T.s < 4 ? 0 : T.s - 4, k1 = T.s < 4 ? 7 : T.s - 4;
-      for (int k = k0; k <= k1; k++) {
-        if (k == T.s) continue;
-        const float sc = __uint_as_float(srcg[k * list_s]) + wrow[k];
-        if (sc > best) { best = sc; bk = k; }
-      }
+    const int k0 = s < 4 ? 0 : s - 4, k1 = s < 4 ? 7 : s - 4;
+    for (int k = k0; k <= k1; k++) {
+      if (k == s) continue;
+      const float sc = __uint_as_float(srcg[k * list_s]) + wrow[k];
+      if (sc > best) { best = sc; bk = k; }
     }
     dst[0] = __float_as_uint(best);
     if (NWD > 0) {
-      if (bk < 0 || bk == T.s) {  // (metric -inf: history is don't-care)
+      if (bk < 0 || bk == s) {  // (metric -inf: history is don't-care)
 #pragma unroll
-        for (int w = 0; w < NWD; w++) dst[(1 + w) * 32] = mine[(1 + w) * NT];
+        for (int w = 0; w < NWD; w++) dst[(1 + w) * 32] = mine[(1 + w) * 32];
       } else {
         uint32_t prev = 0;
 #pragma unroll
         for (int w = 0; w < NWD; w++) {
           uint32_t old = 0;
           if (w < nws) old = srcg[bk * list_s + (1 + w) * TG];
-          dst[(1 + w) * 32] = (old << R.shift) | (w == 0 ? T.drop : (prev >> (32 - R.shift)));
+          dst[(1 + w) * 32] = (old << R.shift) | (w == 0 ? drop : (prev >> (32 - R.shift)));
           prev = old;
         }
       }
     }
     return;
   }
-  Picks<LP> picks;
   int n_acc;
   if (role == 0) {
-    ListView<LP, NWD, 8> V{srcg, mine, wrow, (1 + nws) * LP * TG, nws, (int)R.shift, T.s, T.drop};
-    n_acc = merge_lists<LP, NWD, 8>(picks, V, L, has_src);
-    if (n_acc >= 0) emit_lists<LP, NWD, 8>(dst, picks, n_acc, V, L);
+    ListView<LP, NWD, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), (uint32_t)(1 + nws) * LP * TG * 4u,
+                           nws, (int)R.shift, s, drop};
+    n_acc = merge_lists<LP, NWD, 8>(dst, V, L, true);
   } else {
-    ListView<LP, NWD, 2> V{srcg, mine, wrow, (1 + nws) * LP * TG, nws, (int)R.shift, T.s, T.drop};
-    n_acc = merge_lists<LP, NWD, 2>(picks, V, L, has_src);
-    if (n_acc >= 0) emit_lists<LP, NWD, 2>(dst, picks, n_acc, V, L);
+    ListView<LP, NWD, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), (uint32_t)(1 + nws) * LP * TG * 4u,
+                           nws, (int)R.shift, s, drop};
+    n_acc = merge_lists<LP, NWD, 2>(dst, V, L, true);
   }
   if (n_acc < 0) {  // exact score tie between two list heads: libstdc++ heap order decides
-    exact_merge<LP>(src, mine, post, L, nws, NWD, TG, NT, R.shift, T.drop, T.s, T.src_g);
+    uint32_t *mine_rw = wown + pos;
+    exact_merge<LP>(src, mine_rw, post, L, nws, NWD, TG, 32, R.shift, drop, s, src_g);
     atomicAdd(A.counters, 1ull);
     for (int l = 0; l < L; l++)
-      for (int w = 0; w < 1 + NWD; w++) dst[(w * LP + l) * 32] = mine[(w * LP + l) * NT];
+      for (int w = 0; w < 1 + NWD; w++) dst[(w * LP + l) * 32] = mine_rw[(w * LP + l) * 32];
+  } else {
+    for (int l = n_acc; l < L; l++) dst[l * 32] = 0xff800000u;  // -inf; history of a dead slot is never read
   }
 }
 
