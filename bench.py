@@ -263,7 +263,9 @@ def main():
                          "kernel": "lva_step_fast<LP,NWD> (all step launches)",
                          "algorithmic_bytes_per_step": step_bytes,
                          "avg_launch_us": 1e3 * kernel_ms / max(step_launches, 1),
-                         "traffic": tr.get("dram_bytes_per_launch") if tr else None},
+                         "traffic": tr.get("dram_bytes_per_launch") if tr else None,
+                         "traffic_note": (f"ncu capture of {tr['kernel']}: {tr['dram_bytes_per_launch']} B DRAM vs "
+                                          f"{tr['algorithmic_bytes_same_launch']} B algorithmic for that launch") if tr else None},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -289,7 +289,14 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return cuda_fail("cudaMemGetInfo", e);
   const size_t per_slot = (size_t)h->slot_words * 2 * 4;
   size_t budget = (size_t)(free_b * 0.70);
-  uint32_t slots = params->max_slots ? params->max_slots : 32;
+  // default: enough reads in flight that one step launch is >= ~64 waves of CTAs (small codes are launch-bound otherwise), at least 32
+  uint32_t slots = params->max_slots;
+  if (!slots) {
+    const uint64_t band_rows = std::min<uint64_t>(2ull * h->max_dev, k.nrows);
+    const uint64_t ctas_per_read = std::max<uint64_t>(1, band_rows * 2 * (k.nconv / 32));
+    slots = (uint32_t)std::min<uint64_t>(kMaxSlots, std::max<uint64_t>(32, (64ull * 4 * h->sm_count + ctas_per_read - 1) / ctas_per_read));
+  }
+  if (slots > (uint32_t)kMaxSlots) slots = kMaxSlots;
   if ((size_t)slots * per_slot > budget) slots = (uint32_t)(budget / per_slot);
   if (slots == 0) { lva_destroy(h); return fail(LVA_ERR_OOM, "not enough device memory for one read"); }
   h->n_slots = slots;
@@ -439,8 +446,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
       bo += T;
     }
     CK(cudaMemcpyAsync(h->d_reads.p, rd, sizeof(ReadDev) * ns, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_band.p, band, band_total * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
-    h->timing.h2d_bytes += stage_bytes;
+    h->timing.h2d_bytes += sizeof(ReadDev) * ns;
 
     // ---- initialise the slots ----
     const unsigned long long words = (unsigned long long)ns * 2 * h->slot_words;
@@ -456,8 +462,6 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     a.state = (uint32_t *)h->d_state.p;
     a.slot_words = h->slot_words;
     a.post = d_post;
-    a.reads = (const ReadDev *)h->d_reads.p;
-    a.band = (const uint16_t *)h->d_band.p;
     a.counters = (unsigned long long *)h->d_counters.p;
     a.dev2 = dev2;
     a.code_slot = h->code_slot;
@@ -474,6 +478,10 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
       }
       if (hi <= lo) continue;
       a.t = t;
+      for (uint32_t s = 0; s < active; s++) {
+        a.band_a[s] = band[rd[s].band_off + t];
+        a.post_blk[s] = (uint32_t)(rd[s].post_block + t);
+      }
       if (h->use_fast) {
         cudaError_t e = fast_launch_step(h->LP, h->stream, a, k, lo, hi, active, &h->timing.step_launches);
         if (e != cudaSuccess) { h->err = std::string("fast step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
@@ -562,6 +570,7 @@ static int decode_entry(lva_handle *h, const float *post, bool post_on_device, c
   if (!h) return LVA_ERR_BAD_ARG;
   if (n_reads == 0) return LVA_OK;
   if (!post || !offs || !out_bits || !out_counts) { h->err = "null argument"; return LVA_ERR_BAD_ARG; }
+  if (offs[n_reads] > 0xFFFF0000ull) { h->err = "batch too large (block index must fit 32 bits)"; return LVA_ERR_BAD_ARG; }
   CK(cudaSetDevice(h->device));
   h->timing = lva_timing{};
   CK(cudaMemsetAsync(h->d_counters.p, 0, 64, h->stream));

@@ -47,15 +47,19 @@ struct ReadDev {
   uint32_t band_off;              // offset of its band-start table
 };
 
+constexpr int kMaxSlots = 512;    // reads in flight per handle (3 KB of kernel parameters)
+
+// Everything a step launch needs travels in the kernel parameters (constant bank): a CTA can
+// issue its tile copy without first chasing per-read control data through global memory.
 struct StepArgs {
   uint32_t *state;                // [slot][parity][slot_words]
   unsigned long long slot_words;
   const float *post;
-  const ReadDev *reads;
-  const uint16_t *band;
   unsigned long long *counters;   // [0] exact fallbacks
   uint32_t t, dev2, code_slot;
   uint32_t row_lo, row_hi;        // rows this launch is responsible for
+  uint32_t post_blk[kMaxSlots];   // per active slot: index of the posterior block of this step
+  uint16_t band_a[kMaxSlots];     // per active slot: first in-band row of this step (VCC:677-678)
 };
 
 struct FinalArgs {

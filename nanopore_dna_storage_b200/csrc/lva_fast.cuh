@@ -251,9 +251,7 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   constexpr int NT = kFastThreads, TG = 32;
   extern __shared__ __align__(128) uint32_t smem[];
   const CodeDev &K = c_code[A.code_slot];
-  const ReadDev rd = A.reads[blockIdx.z];
-  if (A.t >= rd.T) return;
-  const uint32_t a = A.band[rd.band_off + A.t];
+  const uint32_t a = A.band_a[blockIdx.z];
   uint32_t bend = a + A.dev2;
   if (bend > K.nrows) bend = K.nrows;
   if (bend > A.row_hi) bend = A.row_hi;
@@ -270,34 +268,24 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   // handles the 64 live flip targets (warps 0-1) and the 64 live flop targets (warps 2-3).
   const bool one_bit = p > 0 && R.shift == 1;
   if (one_bit && cta_role == 1) return;
-  // ---- which target state is mine, and where do its predecessors sit in the tile ----
-  uint32_t c, drop = 0;
+  // ---- which target state is mine (cheap part first: the tile copy is issued before the rest) ----
+  uint32_t c, drop = 0, run, idx, lo;
   int s, src_g = -1, role, pos;  // pos: my word inside the warp's 32-word list rows
   if (p == 0) {
     role = cta_role;
-    c = ((uint32_t)(tid >> 6) << (K.mem - 1)) | (tile * 16u + ((tid >> 2) & 15u));
-    s = (tid & 3) + 4 * role;
+    run = tid >> 6; idx = (tid >> 2) & 15u; lo = tile * 16u + idx;
+    c = (run << (K.mem - 1)) | lo;
     pos = lane;
   } else if (!one_bit) {
     role = cta_role;  // 0: the 128 flip targets of the tile, 1: the 128 flop targets
-    const uint32_t run = warp, idx = lane >> 2, b = lane & 3u;  // a warp = 8 consecutive conv states x 4 bases
-    const uint32_t lo = tile * 8u + idx;
+    run = warp; idx = lane >> 2; lo = tile * 8u + idx;  // a warp = 8 consecutive conv states x 4 bases
     c = (run << (K.mem - 2)) | lo;
-    const uint32_t t = b ^ emitted_base(K, R.block, lo << 2, run & 1u, run >> 1);
-    const uint32_t xy = (R.inv_lin >> (2 * t)) & 3u;
-    src_g = (int)((idx << 2) | xy);
-    drop = (((xy & 1u) << 1) | (xy >> 1)) & R.dropmask;  // bits falling off the register, oldest first
-    s = (int)b + 4 * role;
-    pos = (int)(b * 8u + idx);
+    pos = (int)((lane & 3u) * 8u + idx);
   } else {
     role = warp >> 1;
-    const int u = tid & 63;
-    const uint32_t x = u & 1u, tg = u >> 1, run = tg >> 4, idx = tg & 15u;
-    const uint32_t lo = tile * 16u + idx;
+    const uint32_t tg = (tid & 63) >> 1;
+    run = tg >> 4; idx = tg & 15u; lo = tile * 16u + idx;
     c = (run << (K.mem - 1)) | lo;
-    s = (int)(emitted_base(K, 0, lo << 1, run, 0) ^ (x ? R.lin1 : 0u)) + 4 * role;
-    src_g = (int)((idx << 1) | x);
-    drop = x & R.dropmask;
     pos = lane;
   }
   const bool valid = (c & R.vmask) == R.vval;
@@ -323,11 +311,27 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   if (tid == 0) {
     const uint32_t tile_bytes = p > 0 ? (uint32_t)n_src_lists * (1 + nws) * LP * TG * 4u : 0u;
     mbar_expect_tx(bar, tile_bytes + 160u);
-    bulk_g2s(post, A.post + (rd.post_block + A.t) * 40, 160u, bar);
+    bulk_g2s(post, A.post + (unsigned long long)A.post_blk[blockIdx.z] * 40, 160u, bar);
     if (p > 0) {
       const RowDev S = K.row[p - 1];
       bulk_g2s(src, prv + S.off + (unsigned long long)tile * S.tile_words, tile_bytes, bar);
     }
+  }
+  // ---- the rest of the geometry, while the copies fly: my crf state and predecessor column ----
+  if (p == 0) {
+    s = (tid & 3) + 4 * role;
+  } else if (!one_bit) {
+    const uint32_t b = lane & 3u;
+    const uint32_t t = b ^ emitted_base(K, R.block, lo << 2, run & 1u, run >> 1);
+    const uint32_t xy = (R.inv_lin >> (2 * t)) & 3u;
+    src_g = (int)((idx << 2) | xy);
+    drop = (((xy & 1u) << 1) | (xy >> 1)) & R.dropmask;  // bits falling off the register, oldest first
+    s = (int)b + 4 * role;
+  } else {
+    const uint32_t x = tid & 1u;
+    s = (int)(emitted_base(K, 0, lo << 1, run, 0) ^ (x ? R.lin1 : 0u)) + 4 * role;
+    src_g = (int)((idx << 1) | x);
+    drop = x & R.dropmask;
   }
   constexpr int ROWS = (1 + NWD) * LP;                         // [plane][slot] rows of one list
   uint32_t *wown = own + warp * ROWS * 32;

@@ -267,9 +267,7 @@ __global__ void __launch_bounds__(TG * 8) lva_step_generic(const StepArgs A) {
   constexpr int NT = TG * 8;
   extern __shared__ __align__(128) uint32_t smem[];
   const CodeDev &K = c_code[A.code_slot];
-  const ReadDev rd = A.reads[blockIdx.z];
-  if (A.t >= rd.T) return;
-  const uint32_t a = A.band[rd.band_off + A.t];
+  const uint32_t a = A.band_a[blockIdx.z];
   uint32_t bend = a + A.dev2;
   if (bend > K.nrows) bend = K.nrows;
   if (bend > A.row_hi) bend = A.row_hi;  // a launch may be restricted to rows [row_lo, row_hi)
@@ -293,7 +291,7 @@ __global__ void __launch_bounds__(TG * 8) lva_step_generic(const StepArgs A) {
   uint32_t *cur = A.state + ((unsigned long long)blockIdx.z * 2 + ((A.t + 1u) & 1u)) * A.slot_words;
 
   // ---- stage: posterior block, predecessor tile, own (stay) lists ----
-  if (tid < 10) cp_async16(post + tid * 4, A.post + (rd.post_block + A.t) * 40 + tid * 4);
+  if (tid < 10) cp_async16(post + tid * 4, A.post + (unsigned long long)A.post_blk[blockIdx.z] * 40 + tid * 4);
   if (p > 0) {
     const RowDev S = K.row[p - 1];
     const uint32_t first = tile * TG;  // first predecessor conv state of this CTA
