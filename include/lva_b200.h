@@ -90,6 +90,18 @@ int lva_decode_batch_device(lva_handle *h, const float *post_dev, const uint64_t
                             uint32_t n_reads, uint8_t *out_bits, float *out_scores,
                             uint32_t *out_counts, int32_t *out_status);
 
+/* lva_decode_batch plus the check the reference's drivers run on every list afterwards
+ * (helper.decode_list_CRC_index, helper.py:371-388; framing helper.py:257-264), computed on the GPU
+ * for all candidates: strip the pad bit (pad != 0), left-pad to whole bytes, CRC-8 (poly 0x07, init 0)
+ * of all but the last byte must equal the last byte; index = PRP^-1 of the low 12 bits of the first
+ * two bytes.  out_crc_ok / out_index are [n_reads][list_size] in list order; out_choice[i] is the
+ * first entry with a matching CRC and index < num_oligos, or -1 (any of the three may be NULL).
+ * The list outputs are unchanged: the CRC parameters are not options of the reference tool. */
+int lva_decode_batch_crc(lva_handle *h, const float *post, const uint64_t *block_offsets, uint32_t n_reads,
+                         int32_t pad, uint32_t num_oligos, uint8_t *out_bits, float *out_scores,
+                         uint32_t *out_counts, int32_t *out_status, uint8_t *out_crc_ok,
+                         uint16_t *out_index, int32_t *out_choice);
+
 /* conv_encode (VCC:450-499): msg = msg_len 0/1 bytes; out gets 2 bits per base.  Host only. */
 int lva_encode(uint32_t mem_conv, uint32_t rate, const uint8_t *msg, uint32_t msg_len,
                uint8_t *out_bits, uint32_t out_cap, uint32_t *n_out);

@@ -13,7 +13,7 @@ CLI_PATH = os.path.join(HERE, "_build", "viterbi_nanopore.out")
 LVA_DEFAULT_DEVIATION = 0xFFFFFFFF
 LVA_FLAG_EXACT_ONLY = 1
 
-EXPORTS = ["lva_create", "lva_destroy", "lva_last_error", "lva_decode_batch", "lva_decode_batch_device",
+EXPORTS = ["lva_create", "lva_destroy", "lva_last_error", "lva_decode_batch", "lva_decode_batch_device", "lva_decode_batch_crc",
            "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_version"]
 
 
@@ -67,6 +67,10 @@ def lib() -> C.CDLL:
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                        C.c_void_p, C.c_void_p]
+    L.lva_decode_batch_crc.restype = C.c_int
+    L.lva_decode_batch_crc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
     L.lva_encode.restype = C.c_int
     L.lva_encode.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                              C.POINTER(C.c_uint32)]

@@ -74,6 +74,12 @@ struct lva_handle {
   PinnedBuf h_stage, h_final, h_post;
   std::string err;
   lva_timing timing{};
+  // CRC request of the call in progress (lva_decode_batch_crc)
+  int crc_pad = -1;
+  uint32_t crc_num_oligos = 0;
+  uint8_t *crc_ok_out = nullptr;
+  uint16_t *crc_index_out = nullptr;
+  int32_t *crc_choice_out = nullptr;
   int gen_tg = 32;           // tile width of the generic kernel
   size_t gen_smem = 0;
   bool use_fast = false;
@@ -165,6 +171,7 @@ size_t generic_smem_bytes(uint32_t LP, uint32_t tg, uint32_t nw) {
 struct FinalEntry {
   float score;
   uint32_t id[kMaxIdWords];
+  uint32_t crcw;
 };
 
 }  // namespace
@@ -244,7 +251,7 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   if (h->code_slot < 0) { lva_destroy(h); return fail(LVA_ERR_BAD_ARG, "too many live handles on this device"); }
   CodeDev &d = h->dev_code;
   d.mem = k.mem; d.nconv = k.nconv; d.G0 = k.G[0]; d.G1 = k.G[1]; d.init = k.init; d.fin = k.fin;
-  d.rc = k.rc ? 1 : 0; d.nrows = k.nrows; d.L = h->L; d.LP = h->LP;
+  d.rc = k.rc ? 1 : 0; d.nrows = k.nrows; d.L = h->L; d.LP = h->LP; d.msg_len = k.msg_len; d.pad = 0;
   unsigned long long off = 0;
   for (uint32_t p = 0; p < k.nrows; p++) {
     RowDev &r = d.row[p];
@@ -302,7 +309,7 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   h->n_slots = slots;
   if (!h->d_state.ensure((size_t)slots * per_slot)) { lva_destroy(h); return fail(LVA_ERR_OOM, "state allocation failed"); }
   if (!h->d_reads.ensure(sizeof(ReadDev) * slots) || !h->d_counters.ensure(64) ||
-      !h->d_final.ensure((size_t)slots * 8 * h->LP * (1 + h->nw_last) * 4)) {
+      !h->d_final.ensure((size_t)slots * 8 * h->LP * (2 + h->nw_last) * 4)) {
     lva_destroy(h);
     return fail(LVA_ERR_OOM, "allocation failed");
   }
@@ -399,7 +406,7 @@ int lva_encode(uint32_t mem_conv, uint32_t rate, const uint8_t *msg, uint32_t ms
 static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs, uint32_t n_reads,
                        uint8_t *out_bits, float *out_scores, uint32_t *out_counts, int32_t *out_status) {
   const CodeSpec &k = h->code;
-  const uint32_t L = h->L, LP = h->LP, msg_len = k.msg_len, planes = 1 + h->nw_last;
+  const uint32_t L = h->L, LP = h->LP, msg_len = k.msg_len, planes = 2 + h->nw_last;  // metric, history, CRC word
   const float NEG = -std::numeric_limits<float>::infinity();
 
   std::vector<uint32_t> order;
@@ -509,6 +516,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     f.out = (uint32_t *)h->d_final.p;
     f.code_slot = h->code_slot;
     f.n_slots = ns;
+    f.crc_pad = h->crc_pad;
     const uint32_t nfin = ns * 8 * LP;
     lva_collect_final<<<(nfin + 127) / 128, 128, 0, h->stream>>>(f);
     h->timing.launches += 1;
@@ -540,6 +548,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
             FinalEntry fe;
             fe.score = sc;
             for (uint32_t w = 0; w < h->nw_last; w++) fe.id[w] = e[1 + w];
+            fe.crcw = e[1 + h->nw_last];
             fin.push_back(fe);
           }
         }
@@ -547,6 +556,17 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
                 [](const FinalEntry &p1, const FinalEntry &p2) -> bool { return p1.score > p2.score; });
       if (fin.size() > L) fin.resize(L);
       out_counts[i] = (uint32_t)fin.size();
+      if (h->crc_pad >= 0) {  // helper.decode_list_CRC_index: first entry whose CRC matches and index < num_oligos
+        int32_t choice = -1;
+        for (size_t e = 0; e < fin.size(); e++) {
+          const bool ok = (fin[e].crcw & kCrcOk) != 0;
+          const uint32_t idx = fin[e].crcw & 0xfffu;
+          if (h->crc_ok_out) h->crc_ok_out[(size_t)i * L + e] = ok ? 1 : 0;
+          if (h->crc_index_out) h->crc_index_out[(size_t)i * L + e] = (uint16_t)idx;
+          if (choice < 0 && ok && idx < h->crc_num_oligos) choice = (int32_t)e;
+        }
+        if (h->crc_choice_out) h->crc_choice_out[i] = choice;
+      }
       for (size_t e = 0; e < fin.size(); e++) {
         if (out_scores) out_scores[(size_t)i * L + e] = fin[e].score;
         uint8_t *dst = out_bits + ((size_t)i * L + e) * msg_len;
@@ -602,6 +622,25 @@ int lva_decode_batch(lva_handle *h, const float *post, const uint64_t *block_off
                      uint8_t *out_bits, float *out_scores, uint32_t *out_counts, int32_t *out_status) {
   return decode_entry(h, post, false, block_offsets, n_reads, out_bits, out_scores, out_counts, out_status);
 }
+int lva_decode_batch_crc(lva_handle *h, const float *post, const uint64_t *block_offsets, uint32_t n_reads,
+                         int32_t pad, uint32_t num_oligos, uint8_t *out_bits, float *out_scores,
+                         uint32_t *out_counts, int32_t *out_status, uint8_t *out_crc_ok, uint16_t *out_index,
+                         int32_t *out_choice) {
+  if (!h) return LVA_ERR_BAD_ARG;
+  h->crc_pad = pad ? 1 : 0;
+  h->crc_num_oligos = num_oligos;
+  h->crc_ok_out = out_crc_ok;
+  h->crc_index_out = out_index;
+  h->crc_choice_out = out_choice;
+  if (out_choice) for (uint32_t i = 0; i < n_reads; i++) out_choice[i] = -1;
+  const int st = decode_entry(h, post, false, block_offsets, n_reads, out_bits, out_scores, out_counts, out_status);
+  h->crc_pad = -1;
+  h->crc_ok_out = nullptr;
+  h->crc_index_out = nullptr;
+  h->crc_choice_out = nullptr;
+  return st;
+}
+
 int lva_decode_batch_device(lva_handle *h, const float *post_dev, const uint64_t *block_offsets,
                             uint32_t n_reads, uint8_t *out_bits, float *out_scores, uint32_t *out_counts,
                             int32_t *out_status) {

@@ -37,7 +37,7 @@ struct RowDev {
 
 struct CodeDev {
   uint32_t mem, nconv, G0, G1, init, fin, rc, nrows, L, LP;
-  uint32_t pad[2];
+  uint32_t msg_len, pad;
   RowDev row[kMaxRows];
 };
 
@@ -66,9 +66,13 @@ struct FinalArgs {
   const uint32_t *state;
   unsigned long long slot_words;
   const ReadDev *reads;
-  uint32_t *out;                  // [slot][8][LP][1 + nw_last]
+  uint32_t *out;                  // [slot][8][LP][1 + nw_last + 1]: metric, history words, CRC word
   uint32_t code_slot, n_slots;
+  int32_t crc_pad;                // -1: no CRC check; 0/1: helper.decode_list_CRC_index with pad = 0/1
 };
+
+// CRC word of a candidate: bit 31 = CRC-8 matches, bits 0..11 = oligo index (PRP inverted)
+constexpr uint32_t kCrcOk = 0x80000000u;
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 

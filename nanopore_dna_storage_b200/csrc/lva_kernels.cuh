@@ -348,8 +348,20 @@ __global__ void lva_seed_start(uint32_t *state, unsigned long long slot_words, u
 
 // ---------------------------------------------------------------------------------------------
 // final collection (VCC:806-815): the 8*L entries of (last row, end register, every crf state)
-// of the buffer written by the read's last step, as [slot][crf][slot][1+nw] words.
+// of the buffer written by the read's last step, as [slot][crf][slot][1+nw+1] words, and -- when
+// asked -- the CRC-8 / index check the reference's drivers run on every list entry afterwards
+// (helper.decode_list_CRC_index, /root/reference/helper.py:371-388; message framing
+// helper.py:257-264): strip the pad bit, left-pad the bit string to whole bytes, CRC-8
+// (poly 0x07, init 0) of all but the last byte must equal the last byte; the oligo index is the
+// low 12 bits of the first two bytes pushed back through the PRP x -> 1751 x + 2532 mod 4096.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t crc8_step(uint32_t crc, uint32_t byte) {
+  crc ^= byte;
+#pragma unroll
+  for (int k = 0; k < 8; k++) crc = (crc & 0x80u) ? ((crc << 1) ^ 0x07u) & 0xffu : (crc << 1) & 0xffu;
+  return crc;
+}
+
 __global__ void lva_collect_final(const FinalArgs A) {
   const CodeDev &K = c_code[A.code_slot];
   const uint32_t p = K.nrows - 1;
@@ -362,8 +374,40 @@ __global__ void lva_collect_final(const FinalArgs A) {
   const uint32_t *buf = A.state + ((unsigned long long)slot * 2 + (rd.T & 1u)) * A.slot_words;
   const unsigned long long base = R.off + (unsigned long long)(K.fin >> 5) * R.tile_words + (K.fin & 31u);
   const uint32_t planes = 1 + R.idwords;
-  for (uint32_t w = 0; w < planes; w++)
-    A.out[(unsigned long long)i * planes + w] = buf[base + ((unsigned long long)(s * planes + w) * K.LP + j) * 32];
+  uint32_t v[1 + kMaxIdWords];
+  for (uint32_t w = 0; w < planes; w++) {
+    v[w] = buf[base + ((unsigned long long)(s * planes + w) * K.LP + j) * 32];
+    A.out[(unsigned long long)i * (planes + 1) + w] = v[w];
+  }
+  uint32_t crcw = 0;
+  if (A.crc_pad >= 0 && v[0] != 0xff800000u) {
+    // The history of the end state IS the message: history bit (msg_len-1-b) is message bit b,
+    // and the list line is the message reversed when decoding the reverse-complement strand.
+    const uint32_t M = K.msg_len;
+    const uint32_t n = M - (A.crc_pad ? 1u : 0u);    // the pad bit is the last character of the line
+    const uint32_t nb = (n + 7) / 8, lead = nb * 8 - n;
+    uint32_t crc = 0, last = 0, first2 = 0;
+    for (uint32_t kb = 0; kb < nb; kb++) {
+      uint32_t byte = 0;
+      for (uint32_t r = 0; r < 8; r++) {
+        const uint32_t q = 8 * kb + r;
+        uint32_t bit = 0;
+        if (q >= lead) {
+          const uint32_t b = q - lead;               // character b of the list line
+          const uint32_t hb = K.rc ? b : (M - 1 - b);
+          bit = (v[1 + (hb >> 5)] >> (hb & 31)) & 1u;
+        }
+        byte = (byte << 1) | bit;
+      }
+      if (kb < 2) first2 = (first2 << 8) | byte;
+      if (kb + 1 < nb) crc = crc8_step(crc, byte);
+      else last = byte;
+    }
+    const uint32_t prp = first2 & 0xfffu;
+    const uint32_t idx = (3303u * ((prp + 4096u - 2532u) & 4095u)) & 4095u;
+    crcw = (crc == last ? kCrcOk : 0u) | 0x40000000u | idx;
+  }
+  A.out[(unsigned long long)i * (planes + 1) + planes] = crcw;
 }
 
 }  // namespace lva

@@ -104,6 +104,30 @@ class ListDecoder:
             raise LvaError(int(status[bad]), f"Too small post matrix (read {bad})")
         return bits, scores, counts, status
 
+    def decode_with_crc(self, posts: Sequence[np.ndarray], pad: bool, num_oligos: int):
+        """decode + helper.decode_list_CRC_index on the GPU: per read (bits, scores, crc_ok[n_i],
+        index[n_i], choice) with choice = first entry whose CRC matches and index < num_oligos, or -1."""
+        posts = [np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 40) for p in posts]
+        n = len(posts)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum([p.shape[0] for p in posts])
+        flat = np.concatenate(posts, axis=0)
+        L, M = self.list_size, self.msg_len
+        bits = np.zeros((n, L, M), dtype=np.uint8)
+        scores = np.full((n, L), -np.inf, dtype=np.float32)
+        counts = np.zeros(n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        ok = np.zeros((n, L), dtype=np.uint8)
+        index = np.zeros((n, L), dtype=np.uint16)
+        choice = np.zeros(n, dtype=np.int32)
+        st = self._L.lva_decode_batch_crc(self._h, flat.ctypes.data, offsets.ctypes.data, n, int(pad), num_oligos,
+                                          bits.ctypes.data, scores.ctypes.data, counts.ctypes.data,
+                                          status.ctypes.data, ok.ctypes.data, index.ctypes.data, choice.ctypes.data)
+        if st != 0:
+            raise LvaError(st, self._L.lva_last_error(self._h).decode(errors="replace"))
+        return [(bits[i, :counts[i]].copy(), scores[i, :counts[i]].copy(), ok[i, :counts[i]].astype(bool),
+                 index[i, :counts[i]].copy(), int(choice[i])) for i in range(n)]
+
     def decode(self, posts: Sequence[np.ndarray], strict=True):
         posts = [np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 40) for p in posts]
         offsets = np.zeros(len(posts) + 1, dtype=np.uint64)

@@ -83,3 +83,30 @@ def test_too_small_posterior_is_reported():
         assert ei.value.code == 21
         out = dec.decode([post], strict=False)
         assert out[0][0].shape[0] == 0
+
+
+def test_gpu_crc_sidecar_matches_python_restatement():
+    """north_star (e): CRC-8 / index check of all list entries on the GPU must equal the
+    restatement of helper.decode_list_CRC_index (helper.py:371-388) applied to the emitted lists."""
+    for name, rc in (("C4r2", False), ("C4r3", True)):   # msg_len 180 (no pad) and 181 (pad bit)
+        w = synth.workloads()[name]
+        reads = synth.make_reads(synth.Workload(w.name, w.mem_conv, w.rate, w.msg_len, w.list_size, 20,
+                                                sub=0.004, dele=0.0085, ins=0.0005, seed=w.seed,
+                                                rc_fraction=1.0 if rc else 0.0), 12)
+        with ListDecoder(w.mem_conv, w.rate, w.msg_len, w.list_size, 20, rc=rc) as dec:
+            got = dec.decode_with_crc([r.post for r in reads], pad=w.pad, num_oligos=4096)
+            plain = dec.decode([r.post for r in reads])
+        n_ok = 0
+        for r, (bits, scores, ok, index, choice), (pbits, _) in zip(reads, got, plain):
+            assert np.array_equal(bits, pbits)
+            want_choice = -1
+            for e in range(bits.shape[0]):
+                wok, widx = synth.check_crc_index(bits[e], w.pad)
+                assert bool(ok[e]) == wok and int(index[e]) == widx
+                if want_choice < 0 and wok:
+                    want_choice = e
+            assert choice == want_choice
+            if choice >= 0 and np.array_equal(bits[choice], r.msg):
+                assert int(index[choice]) == r.index % 4096
+                n_ok += 1
+        assert n_ok >= 3, "expected several reads to decode to their framed message"
