@@ -80,6 +80,9 @@ struct lva_handle {
   uint8_t *crc_ok_out = nullptr;
   uint16_t *crc_index_out = nullptr;
   int32_t *crc_choice_out = nullptr;
+  bool survivor = false;     // list size 1: metrics + 4-bit decisions + traceback instead of histories
+  DevBuf d_dec, d_trace;
+  PinnedBuf h_trace;
   int gen_tg = 32;           // tile width of the generic kernel
   size_t gen_smem = 0;
   bool use_fast = false;
@@ -216,6 +219,13 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   h->max_dev = params->max_deviation == LVA_DEFAULT_DEVIATION ? params->msg_len + params->mem_conv + 1
                                                               : params->max_deviation;
   h->nw_last = k.idwords[k.nrows - 1];
+  // List size 1 needs no message identity at all (VCC:715-742 has no de-duplication): keep metrics
+  // only, record one 4-bit decision per state and step, rebuild the message by traceback.
+  h->survivor = h->L == 1 && !(params->flags & LVA_FLAG_EXACT_ONLY);
+  if (h->survivor) {
+    h->nw_last = 0;
+    for (uint32_t p = 0; p < k.nrows; p++) h->code.idwords[p] = 0;
+  }
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -257,8 +267,9 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
     RowDev &r = d.row[p];
     r.off = off;
     r.vmask = k.vmask[p]; r.vval = k.vval[p];
-    r.tile_words = 8u * (1u + k.idwords[p]) * h->LP * 32u;
-    r.block = k.block[p]; r.shift = k.shift[p]; r.idwords = k.idwords[p]; r.dropmask = k.dropmask[p];
+    const uint32_t idw = h->survivor ? 0u : k.idwords[p];
+    r.tile_words = 8u * (1u + idw) * h->LP * 32u;
+    r.block = k.block[p]; r.shift = k.shift[p]; r.idwords = (uint8_t)idw; r.dropmask = k.dropmask[p];
     r.inv_lin = 0; r.lin1 = 0; r.pad0 = r.pad1 = 0; r.pad2 = 0;
     if (p > 0) {  // linear map low predecessor bits -> emitted base (verified bijective by butterfly_structure_ok)
       const uint32_t b0 = host_emitted_base(k, k.block[p], 0, 0, 0);
@@ -346,7 +357,7 @@ int lva_count_work(const lva_handle *h, uint32_t T, lva_work *out) {
       out->state_updates += nst;
       out->edge_acs += nst * (p == 0 ? 1.0 : (k.block[p] == 0 ? 3.0 : 5.0));
       // one read of the previous list + one write of the new list, LP slots of (1+nw) words
-      out->state_bytes += nst * 2.0 * 4.0 * h->LP * (1 + k.idwords[p]);
+      out->state_bytes += nst * 2.0 * 4.0 * h->LP * (1 + k.idwords[p]) + (h->survivor ? nst * 0.5 : 0.0);
     }
   }
   return LVA_OK;
@@ -428,8 +439,18 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
   const uint32_t dev2 = 2u * h->max_dev;
   float acc_kernel = 0.f, acc_d2h = 0.f;
   std::vector<FinalEntry> fin;
-  for (size_t c0 = 0; c0 < order.size(); c0 += h->n_slots) {
-    const uint32_t ns = (uint32_t)std::min<size_t>(h->n_slots, order.size() - c0);
+  const uint32_t dec_rows = (uint32_t)std::min<uint64_t>((uint64_t)dev2 > 0 ? dev2 : 1, k.nrows);
+  size_t chunk_cap = h->n_slots;
+  if (h->survivor && !order.empty()) {  // decisions: T x band rows x conv states words per read in flight
+    const uint64_t Tlongest = offs[order[0] + 1] - offs[order[0]];
+    const uint64_t per_read = Tlongest * dec_rows * k.nconv * 4ull;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget = (uint64_t)((free_b + h->d_dec.cap) * 0.8);
+    chunk_cap = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(h->n_slots, budget / std::max<uint64_t>(per_read, 1)));
+  }
+  for (size_t c0 = 0; c0 < order.size(); c0 += chunk_cap) {
+    const uint32_t ns = (uint32_t)std::min<size_t>(chunk_cap, order.size() - c0);
     // ---- per-slot control + band tables ----
     size_t band_total = 0;
     for (uint32_t s = 0; s < ns; s++) band_total += offs[order[c0 + s] + 1] - offs[order[c0 + s]];
@@ -454,6 +475,17 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     }
     CK(cudaMemcpyAsync(h->d_reads.p, rd, sizeof(ReadDev) * ns, cudaMemcpyHostToDevice, h->stream));
     h->timing.h2d_bytes += sizeof(ReadDev) * ns;
+    unsigned long long dec_slot_words = 0;
+    if (h->survivor) {
+      CK(cudaMemcpyAsync(h->d_band.p, band, band_total * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+      h->timing.h2d_bytes += band_total * sizeof(uint16_t);
+      dec_slot_words = (unsigned long long)Ts[0] * dec_rows * k.nconv;
+      if (!h->d_dec.ensure((size_t)dec_slot_words * ns * 4) || !h->d_trace.ensure((size_t)ns * 12 * 4) ||
+          !h->h_trace.ensure((size_t)ns * 12 * 4)) {
+        h->err = "decision memory allocation failed";
+        return LVA_ERR_OOM;
+      }
+    }
 
     // ---- initialise the slots ----
     const unsigned long long words = (unsigned long long)ns * 2 * h->slot_words;
@@ -472,6 +504,9 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     a.counters = (unsigned long long *)h->d_counters.p;
     a.dev2 = dev2;
     a.code_slot = h->code_slot;
+    a.dec = h->survivor ? (uint32_t *)h->d_dec.p : nullptr;
+    a.dec_slot_words = dec_slot_words;
+    a.dec_rows = dec_rows;
     const uint32_t Tmax = Ts[0];
     uint32_t active = ns;
     for (uint32_t t = 0; t < Tmax; t++) {
@@ -521,6 +556,25 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     lva_collect_final<<<(nfin + 127) / 128, 128, 0, h->stream>>>(f);
     h->timing.launches += 1;
     CK(cudaGetLastError());
+    if (h->survivor) {
+      TraceArgs tr{};
+      tr.state = (const uint32_t *)h->d_state.p;
+      tr.slot_words = h->slot_words;
+      tr.dec = (const uint32_t *)h->d_dec.p;
+      tr.dec_slot_words = dec_slot_words;
+      tr.dec_rows = dec_rows;
+      tr.reads = (const ReadDev *)h->d_reads.p;
+      tr.band = (const uint16_t *)h->d_band.p;
+      tr.out = (uint32_t *)h->d_trace.p;
+      tr.code_slot = h->code_slot;
+      tr.n_slots = ns;
+      tr.crc_pad = h->crc_pad;
+      lva_traceback<<<(ns + 63) / 64, 64, 0, h->stream>>>(tr);
+      h->timing.launches += 1;
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(h->h_trace.p, h->d_trace.p, (size_t)ns * 12 * 4, cudaMemcpyDeviceToHost, h->stream));
+      h->timing.d2h_bytes += (size_t)ns * 12 * 4;
+    }
     const size_t fin_bytes = (size_t)nfin * planes * 4;
     if (!h->h_final.ensure(fin_bytes)) { h->err = "pinned allocation failed"; return LVA_ERR_OOM; }
     CK(cudaEventRecord(h->ev[4], h->stream));
@@ -539,6 +593,17 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     for (uint32_t s = 0; s < ns; s++) {
       const uint32_t i = order[c0 + s];
       fin.clear();
+      if (h->survivor) {  // one entry at most: the traced-back best path
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(h->h_trace.p) + (size_t)s * 12;
+        if (tw[1] == 2u) { h->err = "traceback did not reach the start row"; return LVA_ERR_CUDA; }
+        if (tw[1] == 1u) {
+          FinalEntry fe;
+          memcpy(&fe.score, tw, 4);
+          for (uint32_t w = 0; w < 8; w++) fe.id[w] = tw[4 + w];
+          fe.crcw = tw[2];
+          fin.push_back(fe);
+        }
+      } else
       for (uint32_t crf = 0; crf < 8; crf++)
         for (uint32_t j = 0; j < L; j++) {
           const uint32_t *e = fw + ((size_t)(s * 8 + crf) * LP + j) * planes;

@@ -58,6 +58,10 @@ struct StepArgs {
   unsigned long long *counters;   // [0] exact fallbacks
   uint32_t t, dev2, code_slot;
   uint32_t row_lo, row_hi;        // rows this launch is responsible for
+  // survivor mode (list size 1): 4-bit decisions, 8 per conv state, [slot][t][row - a_t][c] words
+  uint32_t *dec;                  // nullptr unless the handle runs in survivor mode
+  unsigned long long dec_slot_words;
+  uint32_t dec_rows;              // band rows per step in the decision array
   uint32_t post_blk[kMaxSlots];   // per active slot: index of the posterior block of this step
   uint16_t band_a[kMaxSlots];     // per active slot: first in-band row of this step (VCC:677-678)
 };
@@ -69,6 +73,19 @@ struct FinalArgs {
   uint32_t *out;                  // [slot][8][LP][1 + nw_last + 1]: metric, history words, CRC word
   uint32_t code_slot, n_slots;
   int32_t crc_pad;                // -1: no CRC check; 0/1: helper.decode_list_CRC_index with pad = 0/1
+};
+
+struct TraceArgs {
+  const uint32_t *state;          // parity buffers (metrics only in survivor mode)
+  unsigned long long slot_words;
+  const uint32_t *dec;
+  unsigned long long dec_slot_words;
+  uint32_t dec_rows;
+  const ReadDev *reads;
+  const uint16_t *band;           // band-start tables (ReadDev.band_off)
+  uint32_t *out;                  // [slot][12]: metric, found flag, CRC word, pad, 8 message words
+  uint32_t code_slot, n_slots;
+  int32_t crc_pad;
 };
 
 // CRC word of a candidate: bit 31 = CRC-8 matches, bits 0..11 = oligo index (PRP inverted)

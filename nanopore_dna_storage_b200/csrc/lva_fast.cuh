@@ -385,6 +385,25 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
       if (sc > best) { best = sc; bk = k; }
     }
     dst[0] = __float_as_uint(best);
+    if (A.dec != nullptr) {
+      // survivor mode: which predecessor won, 4 bits per state (crf of the source; == s means
+      // "stayed"), the 8 states of a conv state packed into one word: flips low half, flops high
+      const uint32_t code = (uint32_t)(bk < 0 ? s : bk) & 7u;
+      uint32_t v = code << (4 * (s & 3));
+      uint32_t *word = A.dec + (unsigned long long)blockIdx.z * A.dec_slot_words +
+                       ((unsigned long long)A.t * A.dec_rows + (p - a)) * K.nconv + c;
+      unsigned short *half = reinterpret_cast<unsigned short *>(word) + role;
+      if (!one_bit) {  // the 4 lanes lane&~3 .. +3 hold the 4 bases of one conv state
+        const uint32_t gm = 0xFu << (lane & ~3);
+        v |= __shfl_xor_sync(gm, v, 1);
+        v |= __shfl_xor_sync(gm, v, 2);
+        if ((lane & 3) == 0) *half = (unsigned short)v;
+      } else {         // lanes lane&~1, +1 hold the two producible bases of one conv state
+        const uint32_t gm = 0x3u << (lane & ~1);
+        v |= __shfl_xor_sync(gm, v, 1);
+        if ((lane & 1) == 0) *half = (unsigned short)v;
+      }
+    }
     if (NWD > 0) {
       if (bk < 0 || bk == s) {  // (metric -inf: history is don't-care)
 #pragma unroll

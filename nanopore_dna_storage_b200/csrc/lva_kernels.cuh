@@ -362,6 +362,34 @@ __device__ __forceinline__ uint32_t crc8_step(uint32_t crc, uint32_t byte) {
   return crc;
 }
 
+// CRC word (kCrcOk | 0x40000000 | index) of a decoded message given as history words:
+// history bit (msg_len-1-b) is message bit b; the list line is the message, reversed under rc.
+__device__ __forceinline__ uint32_t crc_word_of(const CodeDev &K, const uint32_t *hist, int32_t pad) {
+  const uint32_t M = K.msg_len;
+  const uint32_t n = M - (pad ? 1u : 0u);          // the pad bit is the last character of the line
+  const uint32_t nb = (n + 7) / 8, lead = nb * 8 - n;
+  uint32_t crc = 0, last = 0, first2 = 0;
+  for (uint32_t kb = 0; kb < nb; kb++) {
+    uint32_t byte = 0;
+    for (uint32_t r = 0; r < 8; r++) {
+      const uint32_t q = 8 * kb + r;
+      uint32_t bit = 0;
+      if (q >= lead) {
+        const uint32_t b = q - lead;               // character b of the list line
+        const uint32_t hb = K.rc ? b : (M - 1 - b);
+        bit = (hist[hb >> 5] >> (hb & 31)) & 1u;
+      }
+      byte = (byte << 1) | bit;
+    }
+    if (kb < 2) first2 = (first2 << 8) | byte;
+    if (kb + 1 < nb) crc = crc8_step(crc, byte);
+    else last = byte;
+  }
+  const uint32_t prp = first2 & 0xfffu;
+  const uint32_t idx = (3303u * ((prp + 4096u - 2532u) & 4095u)) & 4095u;
+  return (crc == last ? kCrcOk : 0u) | 0x40000000u | idx;
+}
+
 __global__ void lva_collect_final(const FinalArgs A) {
   const CodeDev &K = c_code[A.code_slot];
   const uint32_t p = K.nrows - 1;
@@ -380,34 +408,79 @@ __global__ void lva_collect_final(const FinalArgs A) {
     A.out[(unsigned long long)i * (planes + 1) + w] = v[w];
   }
   uint32_t crcw = 0;
-  if (A.crc_pad >= 0 && v[0] != 0xff800000u) {
-    // The history of the end state IS the message: history bit (msg_len-1-b) is message bit b,
-    // and the list line is the message reversed when decoding the reverse-complement strand.
-    const uint32_t M = K.msg_len;
-    const uint32_t n = M - (A.crc_pad ? 1u : 0u);    // the pad bit is the last character of the line
-    const uint32_t nb = (n + 7) / 8, lead = nb * 8 - n;
-    uint32_t crc = 0, last = 0, first2 = 0;
-    for (uint32_t kb = 0; kb < nb; kb++) {
-      uint32_t byte = 0;
-      for (uint32_t r = 0; r < 8; r++) {
-        const uint32_t q = 8 * kb + r;
-        uint32_t bit = 0;
-        if (q >= lead) {
-          const uint32_t b = q - lead;               // character b of the list line
-          const uint32_t hb = K.rc ? b : (M - 1 - b);
-          bit = (v[1 + (hb >> 5)] >> (hb & 31)) & 1u;
-        }
-        byte = (byte << 1) | bit;
-      }
-      if (kb < 2) first2 = (first2 << 8) | byte;
-      if (kb + 1 < nb) crc = crc8_step(crc, byte);
-      else last = byte;
-    }
-    const uint32_t prp = first2 & 0xfffu;
-    const uint32_t idx = (3303u * ((prp + 4096u - 2532u) & 4095u)) & 4095u;
-    crcw = (crc == last ? kCrcOk : 0u) | 0x40000000u | idx;
-  }
+  if (A.crc_pad >= 0 && v[0] != 0xff800000u) crcw = crc_word_of(K, v + 1, A.crc_pad);
   A.out[(unsigned long long)i * (planes + 1) + planes] = crcw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Survivor mode (list size 1): batched traceback.  The step kernels kept metrics only and wrote
+// one 4-bit decision per state and step (lva_step_fast<1,0>); one thread per read walks them back
+// from the best end state and rebuilds the message from the register bits of every move.
+// The reference's band quirk is followed exactly: a move at step t into the lowest in-band row
+// may read a value that was last written 3, 5, ... steps earlier (rows below the band are not
+// cleared, VCC:667-687), so the walk jumps to the step that actually produced that value.
+// ---------------------------------------------------------------------------------------------
+__global__ void lva_traceback(const TraceArgs A) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= A.n_slots) return;
+  const CodeDev &K = c_code[A.code_slot];
+  const ReadDev rd = A.reads[slot];
+  const uint32_t m = K.mem, C = K.nconv;
+  uint32_t *out = A.out + (unsigned long long)slot * 12;
+  const uint32_t *buf = A.state + ((unsigned long long)slot * 2 + (rd.T & 1u)) * A.slot_words;
+  uint32_t p = K.nrows - 1, c = K.fin;
+  int s = -1;
+  float best = neg_inf();
+  {
+    const RowDev R = K.row[p];
+    for (int crf = 0; crf < 8; crf++) {  // first strict maximum == stable descending sort, first entry
+      const float sc = __uint_as_float(buf[R.off + (unsigned long long)(c >> 5) * R.tile_words + crf * 32 + (c & 31u)]);
+      if (sc > best) { best = sc; s = crf; }
+    }
+  }
+  out[0] = __float_as_uint(best);
+  out[1] = s >= 0 ? 1u : 0u;
+  out[2] = 0;
+  out[3] = 0;
+  uint32_t full[9];
+  for (int w = 0; w < 9; w++) full[w] = 0;
+  if (s >= 0) {
+    const uint16_t *band = A.band + rd.band_off;
+    const uint32_t *dec = A.dec + (unsigned long long)slot * A.dec_slot_words;
+    int t = (int)rd.T - 1;
+    uint32_t pos = 0;
+    while (p > 0 && t >= 0) {
+      const uint32_t a = band[t];
+      const uint32_t word = dec[((unsigned long long)t * A.dec_rows + (p - a)) * C + c];
+      const int code = (int)((word >> (4 * s)) & 7u);
+      if (code == s) { t--; continue; }  // stayed
+      const RowDev R = K.row[p];
+      const uint32_t sh = R.shift;
+      const uint32_t v = sh == 1 ? (c >> (m - 1)) : ((((c >> (m - 2)) & 1u) << 1) | (c >> (m - 1)));
+      full[pos >> 5] |= v << (pos & 31);
+      if ((pos & 31) + sh > 32) full[(pos >> 5) + 1] |= v >> (32 - (pos & 31));
+      pos += sh;
+      const uint32_t b = (uint32_t)s & 3u, run = c >> (m - sh), lo = c & ((1u << (m - sh)) - 1u);
+      if (sh == 2) {
+        const uint32_t t0 = b ^ emitted_base(K, R.block, lo << 2, run & 1u, run >> 1);
+        c = (lo << 2) | ((R.inv_lin >> (2 * t0)) & 3u);
+      } else {
+        c = (lo << 1) | (b == emitted_base(K, 0, lo << 1, run, 0) ? 0u : 1u);
+      }
+      s = code;
+      p--;
+      t--;
+      while (t >= 0 && band[t] > p) t -= 2;  // stale row: the value read was written earlier in this parity
+    }
+    // `full` now holds all msg_len + m bits, most recent at bit 0; the message history is full >> m
+    uint32_t hist[8];
+    for (int w = 0; w < 8; w++) hist[w] = (full[w] >> m) | (full[w + 1] << (32 - m));
+    for (int w = 0; w < 8; w++) out[4 + w] = hist[w];
+    if (A.crc_pad >= 0) out[2] = crc_word_of(K, hist, A.crc_pad);
+    if (p != 0) out[1] = 2u;  // should not happen: the walk did not reach the start row
+  } else {
+    for (int w = 0; w < 8; w++) out[4 + w] = 0;
+  }
 }
 
 }  // namespace lva

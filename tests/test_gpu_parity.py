@@ -110,3 +110,23 @@ def test_gpu_crc_sidecar_matches_python_restatement():
                 assert int(index[choice]) == r.index % 4096
                 n_ok += 1
         assert n_ok >= 3, "expected several reads to decode to their framed message"
+
+
+def test_survivor_mode_list_size_one(oracle):
+    """L = 1 runs in survivor mode (metrics + 4-bit decisions + batched traceback, north_star d):
+    must equal the oracle and the exact history-carrying path, incl. rc, full band, tight bands with
+    stale rows, sync markers, CRC sidecar, and a batch larger than the slots."""
+    for (mem, rate, msg_len, dev, rc) in [(6, 1, 60, 20, False), (6, 5, 64, 20, True), (8, 3, 41, 4, False),
+                                          (8, 7, 41, None, True), (11, 5, 29, 20, False), (6, 2, 41, 3, False)]:
+        w = synth.Workload("s", mem, rate, msg_len, 1, dev, sub=0.02, dele=0.02, ins=0.01, seed=8100 + mem + rate,
+                           betas=(8.0, 3.0, 2.0))
+        _compare(oracle, w, 9, exact_only=False, rc=rc, max_slots=4, tag=f"survivor m{mem} r{rate} dev{dev} rc{rc}")
+    w = synth.workloads()["C1"]
+    reads = synth.make_reads(w, 6)
+    with ListDecoder(6, 1, 180, 1, 20) as dec:
+        got = dec.decode_with_crc([r.post for r in reads], pad=w.pad, num_oligos=4096)
+    with ListDecoder(6, 1, 180, 1, 20, exact_only=True) as dec:
+        ref = dec.decode_with_crc([r.post for r in reads], pad=w.pad, num_oligos=4096)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and a[4] == b[4]
