@@ -307,12 +307,12 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return cuda_fail("cudaMemGetInfo", e);
   const size_t per_slot = (size_t)h->slot_words * 2 * 4;
   size_t budget = (size_t)(free_b * 0.70);
-  // default: enough reads in flight that one step launch is >= ~64 waves of CTAs (small codes are launch-bound otherwise), at least 32
+  // default: enough reads in flight that one step launch is >= ~64 waves of CTAs (small codes are launch-bound otherwise), at least 64
   uint32_t slots = params->max_slots;
   if (!slots) {
     const uint64_t band_rows = std::min<uint64_t>(2ull * h->max_dev, k.nrows);
     const uint64_t ctas_per_read = std::max<uint64_t>(1, band_rows * 2 * (k.nconv / 32));
-    slots = (uint32_t)std::min<uint64_t>(kMaxSlots, std::max<uint64_t>(32, (64ull * 4 * h->sm_count + ctas_per_read - 1) / ctas_per_read));
+    slots = (uint32_t)std::min<uint64_t>(kMaxSlots, std::max<uint64_t>(64, (64ull * 4 * h->sm_count + ctas_per_read - 1) / ctas_per_read));
   }
   if (slots > (uint32_t)kMaxSlots) slots = kMaxSlots;
   if ((size_t)slots * per_slot > budget) slots = (uint32_t)(budget / per_slot);

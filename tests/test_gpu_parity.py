@@ -130,3 +130,26 @@ def test_survivor_mode_list_size_one(oracle):
     for a, b in zip(got, ref):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
         assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and a[4] == b[4]
+
+
+def test_full_size_headline_config_properties():
+    """BASELINE.json configs[1] at full size (m=11, r=5/6, msg_len=180, L=8, band 20), through
+    properties that need no CPU decode: clean reads round-trip (encode -> posteriors -> decode gives
+    the framed message back on top with a matching CRC and the right index), and the fast path equals
+    the exact heap-order path bit for bit (lists and metrics) on noisy reads."""
+    w = synth.workloads()["C2"]
+    clean = synth.Workload(w.name, 11, 5, 180, 8, 20, seed=4242, betas=(8.0,))
+    reads = synth.make_reads(clean, 6)
+    with ListDecoder(11, 5, 180, 8, 20) as dec:
+        got = dec.decode_with_crc([r.post for r in reads], pad=clean.pad, num_oligos=4096)
+        noisy = synth.make_reads(w, 3, start=77)
+        fast = dec.decode([r.post for r in noisy])
+    for r, (bits, scores, ok, index, choice) in zip(reads, got):
+        assert bits.shape[0] == 8 and np.array_equal(bits[0], r.msg)
+        assert choice == 0 and ok[0] and int(index[0]) == r.index
+        assert np.all(np.diff(scores) <= 0), "list must be sorted by metric"
+        assert len({b.tobytes() for b in bits}) == 8, "list entries must be distinct messages"
+    with ListDecoder(11, 5, 180, 8, 20, exact_only=True, max_slots=4) as dec:
+        exact = dec.decode([r.post for r in noisy])
+    for (b1, s1), (b2, s2) in zip(fast, exact):
+        assert np.array_equal(b1, b2) and np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
