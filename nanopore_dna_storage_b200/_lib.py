@@ -7,7 +7,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_build", "liblva_b200.so")
+# LVA_B200_LIB: developer override to A/B two builds of the same CUDA library (never a CPU path)
+LIB_PATH = os.environ.get("LVA_B200_LIB") or os.path.join(HERE, "_build", "liblva_b200.so")
 CLI_PATH = os.path.join(HERE, "_build", "viterbi_nanopore.out")
 
 LVA_DEFAULT_DEVIATION = 0xFFFFFFFF

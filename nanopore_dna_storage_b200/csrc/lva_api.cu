@@ -83,6 +83,8 @@ struct lva_handle {
   bool survivor = false;     // list size 1: metrics + 4-bit decisions + traceback instead of histories
   DevBuf d_dec, d_trace;
   PinnedBuf h_trace;
+  int gen_tg = 32;           // tile width of the generic kernel
+  size_t gen_smem = 0;
   bool use_fast = false;
 };
 
@@ -137,23 +139,36 @@ bool butterfly_structure_ok(const CodeSpec &k) {
   return true;
 }
 
-template <int LP>
+template <int LP, int TG>
 cudaError_t launch_generic(const lva_handle *h, dim3 grid, const StepArgs &a) {
-  lva_step_generic<LP><<<grid, 256, 0, h->stream>>>(a);
+  lva_step_generic<LP, TG><<<grid, TG * 8, h->gen_smem, h->stream>>>(a);
   return cudaGetLastError();
 }
+template <int LP, int TG>
+cudaError_t prep_generic(size_t smem) {
+  return cudaFuncSetAttribute(lva_step_generic<LP, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
 
+#define LVA_GENERIC_CASES(X) \
+  X(1, 32) X(2, 32) X(4, 32) X(8, 32) X(16, 32) X(16, 16) X(32, 16) X(32, 8) X(64, 8) X(64, 4)
+
+cudaError_t generic_prepare(const lva_handle *h) {
+#define X(lp, tg) \
+  if (h->LP == lp && h->gen_tg == tg) return prep_generic<lp, tg>(h->gen_smem);
+  LVA_GENERIC_CASES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
 cudaError_t generic_launch(const lva_handle *h, dim3 grid, const StepArgs &a) {
-  switch (h->LP) {
-    case 1: return launch_generic<1>(h, grid, a);
-    case 2: return launch_generic<2>(h, grid, a);
-    case 4: return launch_generic<4>(h, grid, a);
-    case 8: return launch_generic<8>(h, grid, a);
-    case 16: return launch_generic<16>(h, grid, a);
-    case 32: return launch_generic<32>(h, grid, a);
-    case 64: return launch_generic<64>(h, grid, a);
-    default: return cudaErrorInvalidValue;
-  }
+#define X(lp, tg) \
+  if (h->LP == lp && h->gen_tg == tg) return launch_generic<lp, tg>(h, grid, a);
+  LVA_GENERIC_CASES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+size_t generic_smem_bytes(uint32_t LP, uint32_t tg, uint32_t nw) {
+  return 256 + ((size_t)8 * (1 + nw) * LP * tg + (size_t)(1 + nw) * LP * tg * 8) * 4;
 }
 
 struct FinalEntry {
@@ -253,11 +268,9 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
     r.off = off;
     r.vmask = k.vmask[p]; r.vval = k.vval[p];
     const uint32_t idw = h->survivor ? 0u : k.idwords[p];
-    r.planes = idw > 0 ? 2 : 1;                          // metric (+ history hash)
-    r.hist_off = 8u * r.planes * h->LP * 32u;
-    r.tile_words = 8u * h->LP * 32u * (r.planes + idw);
+    r.tile_words = 8u * (1u + idw) * h->LP * 32u;
     r.block = k.block[p]; r.shift = k.shift[p]; r.idwords = (uint8_t)idw; r.dropmask = k.dropmask[p];
-    r.inv_lin = 0; r.lin1 = 0; r.pad1 = 0;
+    r.inv_lin = 0; r.lin1 = 0; r.pad0 = r.pad1 = 0; r.pad2 = 0;
     if (p > 0) {  // linear map low predecessor bits -> emitted base (verified bijective by butterfly_structure_ok)
       const uint32_t b0 = host_emitted_base(k, k.block[p], 0, 0, 0);
       for (uint32_t xy = 0; xy < (1u << k.shift[p]); xy++) {
@@ -273,6 +286,18 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
     return cuda_fail("cudaMemcpyToSymbol", e);
 
   // ---- kernel selection ----
+  h->gen_tg = 0;
+  for (int tg : {32, 16, 8, 4}) {
+    bool have = false;
+#define X(lp, tgc) if (h->LP == lp && tg == tgc) have = true;
+    LVA_GENERIC_CASES(X)
+#undef X
+    if (!have) continue;
+    size_t sm = generic_smem_bytes(h->LP, tg, h->nw_last);
+    if (sm <= (size_t)prop.sharedMemPerBlockOptin) { h->gen_tg = tg; h->gen_smem = sm; break; }
+  }
+  if (!h->gen_tg) { lva_destroy(h); return fail(LVA_ERR_LIST_SIZE, "list_size x msg_len too large for shared memory"); }
+  if ((e = generic_prepare(h)) != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(generic)", e);
   h->use_fast = !(params->flags & LVA_FLAG_EXACT_ONLY) && fast_supported(h->LP, h->nw_last);
   if (h->use_fast && (e = fast_prepare(h->LP, h->nw_last)) != cudaSuccess)
     return cuda_fail("cudaFuncSetAttribute(fast)", e);
@@ -332,8 +357,7 @@ int lva_count_work(const lva_handle *h, uint32_t T, lva_work *out) {
       out->state_updates += nst;
       out->edge_acs += nst * (p == 0 ? 1.0 : (k.block[p] == 0 ? 3.0 : 5.0));
       // one read of the previous list + one write of the new list, LP slots of (1+nw) words
-      // one read of the previous list + one write of the new list: metric, hash, history words
-      out->state_bytes += nst * 2.0 * 4.0 * h->LP * ((k.idwords[p] ? 2 : 1) + k.idwords[p]) + (h->survivor ? nst * 0.5 : 0.0);
+      out->state_bytes += nst * 2.0 * 4.0 * h->LP * (1 + k.idwords[p]) + (h->survivor ? nst * 0.5 : 0.0);
     }
   }
   return LVA_OK;
@@ -511,7 +535,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
           const uint32_t st = band[rd[s].band_off + t];
           span = std::max(span, band_end(st, k.nrows, h->max_dev) - st);
         }
-        dim3 grid(k.nconv / 32, span, active);
+        dim3 grid(k.nconv / h->gen_tg, span, active);
         cudaError_t e = generic_launch(h, grid, a);
         if (e != cudaSuccess) { h->err = std::string("generic step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
         h->timing.step_launches++;

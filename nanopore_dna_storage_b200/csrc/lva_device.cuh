@@ -1,23 +1,17 @@
 // Device-side data model shared by the trellis kernels.
 //
 // State layout in HBM ("tile-transposed"): a parity buffer holds, for every trellis row p
-// (= nstate_pos index of the reference, VCC:74), C/32 tiles of 32 consecutive conv states.  A
-// tile of a row whose list entries carry nw history words is one contiguous chunk of two regions:
+// (= nstate_pos index of the reference, VCC:74), C/32 tiles of 32 consecutive conv states.
+// Inside a tile the 32 conv states are the FASTEST index:
 //
-//   planes   [crf s][plane][slot][conv g]      plane 0 = path metric (fp32 bits)
-//                                              plane 1 = 32-bit hash of the message history
-//                                              (only when nw > 0)
-//   history  [crf s][slot][conv g][word w]     the message bits that have already left the conv
-//                                              register, LSW first (only when nw > 0)
+//     word(p, c, s, plane, slot) = row[p].off + (c >> 5) * row[p].tile_words
+//                                + ((s * (1 + nw_p) + plane) * LP + slot) * 32 + (c & 31)
 //
-//   word(p,c,s,plane,slot) = row.off + (c>>5)*row.tile_words + ((s*P + plane)*LP + slot)*32 + (c&31)
-//   hist(p,c,s,slot,w)     = row.off + (c>>5)*row.tile_words + row.hist_off + ((s*LP + slot)*32 + (c&31))*nw + w
-//
-// The step kernel stages ONLY the planes region (one contiguous TMA bulk copy per CTA, 16 KB
-// whatever nw is): in shared memory bank == conv state, so the 32 lanes of a warp, which always
-// address 32 different predecessor conv states, never conflict.  History words are touched only
-// when an entry is accepted (or a hash match must be verified): they are read from and written to
-// HBM directly, one 32-byte sector per entry.
+// plane 0 = path metric (fp32 bits), planes 1..nw_p = message history words (the message bits
+// that have already left the conv register, LSW first; the register itself is the state index).
+// A tile is one contiguous chunk, so a CTA stages its 32 predecessor conv states with ONE bulk
+// copy, shared-memory bank == conv state (conflict-free for any slot / plane / crf pattern), and
+// a warp's 4-byte stores land as complete 32-byte sectors.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -32,13 +26,13 @@ constexpr int kTileGroups = 32;  // conv states per HBM tile
 struct RowDev {
   unsigned long long off;  // word offset of the row inside a parity buffer
   uint32_t vmask, vval;    // conv state reachable iff (c & vmask) == vval   (VCC:944-978)
-  uint32_t tile_words;     // 8 * LP * 32 * (planes + idwords)
-  uint32_t hist_off;       // words from the tile start to its history region (= 8 * planes * LP * 32)
+  uint32_t tile_words;     // 8 * (1 + idwords) * LP * 32
   uint8_t block, shift, idwords, dropmask;
   // The base a conv transition emits is XOR-linear in the predecessor's low `shift` bits xy:
   // base(c', xy) = base(c', 0) ^ lin[xy].  inv_lin packs, for t = 0..3, the xy with lin[xy] == t
   // (2 bits each; one-bit steps: only t in {0, lin[1]} exist) and lin1 = lin[1] for one-bit steps.
-  uint8_t inv_lin, lin1, planes, pad1;  // planes: 2 (metric, hash) when idwords > 0, else 1
+  uint8_t inv_lin, lin1, pad0, pad1;
+  uint32_t pad2;
 };
 
 struct CodeDev {
@@ -98,10 +92,5 @@ struct TraceArgs {
 constexpr uint32_t kCrcOk = 0x80000000u;
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
-
-// hash of an extended history from the hash of its predecessor: any deterministic function works
-// (equal histories are built by equal extension sequences, so they get equal hashes); a hash match
-// is never trusted -- it is verified word by word.
-__device__ __forceinline__ uint32_t mix_hash(uint32_t h, uint32_t drop) { return h * 0x9E3779B1u + drop + 1u; }
 
 }  // namespace lva

@@ -5,28 +5,22 @@
 // (blockIdx.x & 1): role 0 computes the 128 flip targets fed by the tile, role 1 the 128 flop
 // targets.  Flip targets merge 8 lists, flop targets 2, so giving them separate CTAs lets the
 // short ones retire and free their SM slot instead of idling beside the long ones.
-//   * only the PLANES region of the predecessor tile (metric + history hash, 16 KB whatever the
-//     history width; flop CTAs need just its first half, the four flip lists) is staged: ONE
-//     contiguous TMA bulk copy (cp.async.bulk, SASS UBLKCP) into shared memory, completion on an
-//     mbarrier; the step's 40 transition scores ride the same barrier.  ~25 KB of shared memory
-//     per CTA -> 9 CTAs / 36 warps per SM for every row of the trellis;
+//   * the predecessor tile is ONE contiguous chunk (flop CTAs need only its first half, the
+//     four flip lists) -> a single TMA bulk copy (cp.async.bulk, SASS UBLKCP) into shared
+//     memory, completion on an mbarrier; the step's 40 transition scores ride the same barrier;
 //   * each thread owns one target state (p, c, s); the 32 lanes of a warp read 32 DIFFERENT
 //     predecessor conv states, which in the tile-transposed layout are 32 different banks ->
 //     no bank conflicts whatever the (crf, slot, plane) pattern;
-//   * the new list is built by a flat k-way merge (one candidate popped per trip by every lane).
-//     De-duplication works on the stored 32-bit history hash: a one-byte signature per accepted
-//     entry is kept in registers, signature matches are checked against the full hash; equal
-//     hashes are PRESUMED duplicates and verified word by word against the histories in HBM, off
-//     the critical path (loads issued at detection, compared one event later);
-//   * history words never enter shared memory: when an entry is accepted its predecessor's words
-//     are loaded from HBM (one sector), extended by the bits leaving the register, and stored to
-//     the new list one accept later, so the merge never waits for them;
-//   * whenever two list heads tie exactly for the maximum, or a presumed duplicate fails its
-//     verification, the thread re-runs that state through exact_merge(), which reproduces
-//     libstdc++'s heap order (VCC:762-795).  Without a tie the pop sequence of any correct k-way
-//     merge equals the reference's, so the fast path is bit-identical by construction;
+//   * the new list is built by a flat k-way merge (one candidate popped per trip by every lane)
+//     with de-duplication on the message history: a one-word XOR signature per accepted entry
+//     is kept in registers, signature matches (rare: ~1 per state) are verified word by word;
+//     accepted entries are kept as (list, slot) descriptors and materialised when stored;
 //   * states that no conv transition can produce (two of the four bases of every conv state on
-//     rows entered by a one-bit step) are never touched: they keep their initial -inf.
+//     rows entered by a one-bit step) are never touched: they keep their initial -inf;
+//   * whenever two list heads tie exactly for the maximum the thread re-runs that state through
+//     exact_merge(), which reproduces libstdc++'s heap order (VCC:762-795).  Without a tie the
+//     pop sequence of any correct k-way merge equals the reference's, so the fast path is
+//     bit-identical by construction.
 #pragma once
 #include "lva_kernels.cuh"
 
@@ -34,31 +28,26 @@ namespace lva {
 
 constexpr int kFastThreads = 128;
 
+// Everything a thread needs to address the lists it merges.  Staged lists -- the predecessor
+// tile and the warp's own (stay) lists -- share one shape: [plane][slot] rows of 32 words.
+//   NL = 8 (flip target s < 4): list i is predecessor crf i, except list s which is the state's
+//                               own (stay) list; all weights come from posterior row s.
+//   NL = 2 (flop target s >= 4): list 0 = own list (column s of row 4), list 1 = the flip state
+//                               s-4 of the predecessor conv state (column s-4 of row 4).
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float(lds_u32(addr)); }
-__device__ __forceinline__ uint32_t ldg_nc(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
 
-// Everything a thread needs to address the lists it merges.  Shared-memory accesses go through
-// 32-bit shared-window addresses computed once per thread.
-//   NL = 8 (flip target s < 4): list i is predecessor crf i, except list s which is the state's
-//                               own (stay) list; all weights come from posterior row s.
-//   NL = 2 (flop target s >= 4): list 0 = own list (column s of row 4), list 1 = the flip state
-//                               s-4 of the predecessor conv state (column s-4 of row 4).
+// All list accesses go through 32-bit shared-window addresses computed once per thread (plain
+// generic pointers made the compiler rebuild the shared window base inside the merge loop).
 template <int LP, int NWD, int NL>
 struct ListView {
   static constexpr uint32_t SS = 32 * 4, PS = LP * 32 * 4;  // slot / plane stride in bytes
   uint32_t srcg, mine, wrow;  // shared addresses: my predecessor column, my own list, my score row
-  uint32_t list_s;            // bytes between the crf lists of the staged predecessor planes
-  const uint32_t *gsrc;       // HBM: history of entry (crf k, slot j) of my predecessor at gsrc[((k*LP+j)*32)*nws + w]
-  const uint32_t *gown;       // HBM: history of entry j of my own previous list at gown[j*32*NWD + w]
+  uint32_t list_s;            // bytes between the crf lists of the predecessor tile
   int nws, sh, s;
   uint32_t drop;
 
@@ -70,44 +59,28 @@ struct ListView {
   __device__ __forceinline__ float score(int i, int j) const {
     return lds_f32(base(i) + (uint32_t)j * SS) + lds_f32(wrow + 4u * (uint32_t)crf_of(i));
   }
-  // hash of the history entry j of list i would carry at the target
-  __device__ __forceinline__ uint32_t hash(int i, int j) const {
+  // message history entry j of list i would carry at the target (NWD words)
+  __device__ __forceinline__ void history(int i, int j, uint32_t (&cand)[NWD > 0 ? NWD : 1]) const {
+    if (NWD == 0) return;
     const bool st = is_stay(i);
-    uint32_t h = 0;
-    if (st || nws > 0) h = lds_u32(base(i) + PS + (uint32_t)j * SS);
-    return st ? h : mix_hash(h, drop);
-  }
-};
-
-// History words of one list entry on their way from HBM: loaded when the entry is accepted (or a
-// presumed duplicate needs verifying), finished (extended by the bits that left the register) when
-// they are consumed one event later.
-template <int NWD>
-struct Fetched {
-  uint32_t old[NWD > 0 ? NWD : 1];
-  int sh_e;
-  uint32_t drop_e;
-  template <int LP, int NL>
-  __device__ __forceinline__ void load(const ListView<LP, NWD, NL> &V, int i, int j) {
-    const bool st = V.is_stay(i);
-    const uint32_t *p = st ? V.gown + j * 32 * NWD : V.gsrc + ((V.crf_of(i) * LP + j) * 32) * V.nws;
-    const int n = st ? NWD : V.nws;
+    const uint32_t b = base(i) + (uint32_t)j * SS;
+    const int sh_e = st ? 0 : sh;
+    const uint32_t drop_e = st ? 0u : drop;
+    const bool top_word = st || nws == NWD;  // does this list carry NWD words already?
+    uint32_t old[NWD > 0 ? NWD : 1];
 #pragma unroll
     for (int w = 0; w < NWD; w++) {
       old[w] = 0;
-      if (w < NWD - 1 || n == NWD) old[w] = ldg_nc(p + w);
+      if (w < NWD - 1 || top_word) old[w] = lds_u32(b + (1 + w) * PS);
     }
-    sh_e = st ? 0 : V.sh;
-    drop_e = st ? 0u : V.drop;
-  }
-  __device__ __forceinline__ void finish(uint32_t (&out)[NWD > 0 ? NWD : 1]) const {
-    out[0] = (old[0] << sh_e) | drop_e;
+    cand[0] = (old[0] << sh_e) | drop_e;
 #pragma unroll
-    for (int w = 1; w < NWD; w++) out[w] = __funnelshift_l(old[w - 1], old[w], sh_e);
+    for (int w = 1; w < NWD; w++) cand[w] = __funnelshift_l(old[w - 1], old[w], sh_e);
   }
 };
 
-// Accepted entries are remembered as (list, slot) descriptors, 8 bits each.
+// Accepted entries are remembered as (list, slot) descriptors, 8 bits each: a signature match is
+// verified by re-deriving the accepted entry's history from the staged lists.
 template <int LP>
 struct Picks {
   static_assert(LP <= 16, "descriptor words cover at most 16 slots");
@@ -133,7 +106,7 @@ struct Picks {
 
 // One-byte signatures of the accepted entries, four per register.  match() returns a mask with
 // bit (8*(a&3) + (a>>2)) set for every accepted slot a whose signature MAY equal `sig8` (the
-// zero-byte test can flag a byte above a true match; callers check the full hash), live slots only.
+// zero-byte test can flag a byte above a true match; callers verify), restricted to live slots.
 template <int LP>
 struct SigBytes {
   static constexpr int NR = (LP + 3) / 4;
@@ -186,19 +159,19 @@ __device__ __forceinline__ void select_head(const float (&h)[NL], float &best, i
 // Flat k-way merge with de-duplication (VCC:743-800).  Each trip handles one popped candidate;
 // the selection of the NEXT candidate (advance the popped list, arg-max over the heads) does not
 // depend on the accept/duplicate decision of the current one, so both chains sit in one loop
-// body and overlap.  An accepted candidate's metric and hash are stored to the new list right
-// away (lanes accept in lock step unless one of them met a duplicate, so a warp's stores still
-// land as complete sectors almost always); its history follows one accept later.
-// dplanes / dhist: my new list in the current parity buffer (planes region / history region).
-// Returns the number of accepted entries, or -1 if the state must be redone exactly (two heads
-// tied for the maximum, or a presumed duplicate turned out to be a hash collision).
+// body and overlap.  An accepted candidate is stored to the new list in HBM right away: lanes
+// accept in lock step unless one of them met a duplicate (about once per state), so the stores
+// of a warp still land as complete sectors almost always.  Exact ties are detected lazily: two
+// consecutive pops with equal metric from different lists, or a head equal to the last popped
+// metric when the loop ends.
+// Returns the number of accepted entries, or -1 on a tie (caller falls back to exact_merge and
+// overwrites whatever was stored).
 template <int LP, int NWD, int NL>
-__device__ __forceinline__ int merge_lists(uint32_t *dplanes, uint32_t *dhist, const ListView<LP, NWD, NL> &V,
-                                           int L) {
+__device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD, NL> &V, int L, bool has_src) {
   const float NEG = neg_inf();
   float h[NL];
 #pragma unroll
-  for (int i = 0; i < NL; i++) h[i] = V.score(i, 0);
+  for (int i = 0; i < NL; i++) h[i] = (V.is_stay(i) || has_src) ? V.score(i, 0) : NEG;
   float best;
   int i;
   select_head<NL>(h, best, i);
@@ -210,22 +183,20 @@ __device__ __forceinline__ int merge_lists(uint32_t *dplanes, uint32_t *dhist, c
   uint32_t ptrs = 0;  // 4-bit read position per list
   int l = 0, prev_i = -1;
   float prev_best = __int_as_float(0x7f800000);  // +inf: never equals a metric
-  bool redo = false;
-  Fetched<NWD> em, va, vb;       // history in flight: of the last accepted entry / of a presumed duplicate pair
-  bool em_on = false, v_on = false;
-  uint32_t *em_dst = dhist;
+  bool tie = false;
   while (true) {
     const int j = (ptrs >> (4 * i)) & 15;
-    redo = redo || (best == prev_best && i != prev_i);
+    tie = tie || (best == prev_best && i != prev_i);
     prev_best = best;
     prev_i = i;
-    // ---- chain A: hash of the current candidate ----
-    uint32_t hcur = 0, sig8 = 0;
-    if (NWD > 0) {
-      hcur = V.hash(i, j);
-      sig8 = hcur ^ (hcur >> 16);
-      sig8 = (sig8 ^ (sig8 >> 8)) & 0xffu;
-    }
+    // ---- chain A: history and signature of the current candidate ----
+    uint32_t cand[NWD > 0 ? NWD : 1];
+    V.history(i, j, cand);
+    uint32_t csig = 0;
+#pragma unroll
+    for (int w = 0; w < NWD; w++) csig ^= cand[w];
+    csig ^= csig >> 16;
+    csig = (csig ^ (csig >> 8)) & 0xffu;
     // ---- chain B: advance the popped list and select the next candidate ----
     float nh = NEG;
     if (j + 1 < L) {
@@ -238,51 +209,31 @@ __device__ __forceinline__ int merge_lists(uint32_t *dplanes, uint32_t *dhist, c
     int ni;
     select_head<NL>(h, nbest, ni);
     // ---- chain A continued: de-duplicate, accept ----
-    bool dup = false;
-    uint32_t dmatch = 0;
+    bool dup;
     if (NWD == 0) {
       dup = l > 0;
     } else {
-      uint32_t m = sigs.match(sig8);
+      uint32_t m = sigs.match(csig);
+      dup = false;
       while (m != 0 && !dup) {
         const int a = SigBytes<LP>::slot_of_bit(__ffs(m) - 1);
         m &= m - 1u;
-        dmatch = picks.get(a);
-        dup = V.hash((int)(dmatch >> 4), (int)(dmatch & 15u)) == hcur;
+        const uint32_t d = picks.get(a);
+        uint32_t acc[NWD > 0 ? NWD : 1];
+        V.history((int)(d >> 4), (int)(d & 15u), acc);
+        uint32_t diff = 0;
+#pragma unroll
+        for (int w = 0; w < NWD; w++) diff |= acc[w] ^ cand[w];
+        dup = diff == 0;
       }
     }
-    if (dup) {
-      if (NWD > 0) {  // presumed duplicate: verify the histories, one event later
-        if (v_on) {
-          uint32_t x[NWD > 0 ? NWD : 1], y[NWD > 0 ? NWD : 1];
-          va.finish(x);
-          vb.finish(y);
-          uint32_t diff = 0;
+    if (!dup) {
+      dst[0] = __float_as_uint(best);  // dst walks the slots of the new list
 #pragma unroll
-          for (int w = 0; w < NWD; w++) diff |= x[w] ^ y[w];
-          redo = redo || diff != 0;
-        }
-        va.load(V, i, j);
-        vb.load(V, (int)(dmatch >> 4), (int)(dmatch & 15u));
-        v_on = true;
-      }
-    } else {
-      dplanes[0] = __float_as_uint(best);  // dplanes walks the slots of the new list
-      if (NWD > 0) {
-        dplanes[LP * 32] = hcur;
-        if (em_on) {
-          uint32_t x[NWD > 0 ? NWD : 1];
-          em.finish(x);
-#pragma unroll
-          for (int w = 0; w < NWD; w++) em_dst[w] = x[w];
-        }
-        em.load(V, i, j);
-        em_dst = dhist + l * 32 * NWD;
-        em_on = true;
-        picks.set(l, (uint32_t)((i << 4) | j));
-        sigs.insert(l, sig8);
-      }
-      dplanes += 32;
+      for (int w = 0; w < NWD; w++) dst[(1 + w) * LP * 32] = cand[w];
+      dst += 32;
+      picks.set(l, (uint32_t)((i << 4) | j));
+      sigs.insert(l, csig);
       l++;
       if (l == L || NWD == 0) break;  // NWD == 0: every further candidate carries the same (empty) history
     }
@@ -290,32 +241,14 @@ __device__ __forceinline__ int merge_lists(uint32_t *dplanes, uint32_t *dhist, c
     best = nbest;
     i = ni;
   }
-  if (NWD > 0) {
-    if (em_on) {
-      uint32_t x[NWD > 0 ? NWD : 1];
-      em.finish(x);
 #pragma unroll
-      for (int w = 0; w < NWD; w++) em_dst[w] = x[w];
-    }
-    if (v_on) {
-      uint32_t x[NWD > 0 ? NWD : 1], y[NWD > 0 ? NWD : 1];
-      va.finish(x);
-      vb.finish(y);
-      uint32_t diff = 0;
-#pragma unroll
-      for (int w = 0; w < NWD; w++) diff |= x[w] ^ y[w];
-      redo = redo || diff != 0;
-    }
-  }
-#pragma unroll
-  for (int i2 = 0; i2 < NL; i2++) redo = redo || (h[i2] == prev_best);
-  return redo ? -1 : l;
+  for (int i2 = 0; i2 < NL; i2++) tie = tie || (h[i2] == prev_best);
+  return tie ? -1 : l;
 }
 
 template <int LP, int NWD>
 __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) {
-  constexpr int TG = 32;
-  constexpr int PD = NWD > 0 ? 2 : 1;  // planes of the target row: metric (+ hash)
+  constexpr int NT = kFastThreads, TG = 32;
   extern __shared__ __align__(128) uint32_t smem[];
   const CodeDev &K = c_code[A.code_slot];
   const uint32_t a = A.band_a[blockIdx.z];
@@ -337,7 +270,7 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   if (one_bit && cta_role == 1) return;
   // ---- which target state is mine (cheap part first: the tile copy is issued before the rest) ----
   uint32_t c, drop = 0, run, idx, lo;
-  int s, src_g = 0, role, pos;  // pos: my word inside the warp's 32-word list rows
+  int s, src_g = -1, role, pos;  // pos: my word inside the warp's 32-word list rows
   if (p == 0) {
     role = cta_role;
     run = tid >> 6; idx = (tid >> 2) & 15u; lo = tile * 16u + idx;
@@ -360,12 +293,10 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);          // bytes 0..7
   float *post = reinterpret_cast<float *>(smem + 4);           // bytes 16..175
   uint32_t *src = smem + 64;                                   // byte 256
-  const RowDev S = K.row[p > 0 ? p - 1 : 0];
-  const int nws = p > 0 ? S.idwords : 0;
-  const int PSRC = nws > 0 ? 2 : 1;                            // planes of the predecessor row
-  // flop-only CTAs read just the flip lists 0..3 = the first half of the planes region
+  const int nws = p > 0 ? K.row[p - 1].idwords : 0;
+  // flop-only CTAs read just the flip lists 0..3 = the first half of the tile
   const int n_src_lists = (p > 0 && !one_bit && role == 1) ? 4 : 8;
-  uint32_t *own = src + n_src_lists * PSRC * LP * TG;          // own lists, per warp [plane][slot][32]
+  uint32_t *own = src + n_src_lists * (1 + nws) * LP * TG;     // stay lists, per warp [plane][slot][32]
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
@@ -378,10 +309,13 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
 
   // ---- stage ----
   if (tid == 0) {
-    const uint32_t tile_bytes = p > 0 ? (uint32_t)n_src_lists * PSRC * LP * TG * 4u : 0u;
+    const uint32_t tile_bytes = p > 0 ? (uint32_t)n_src_lists * (1 + nws) * LP * TG * 4u : 0u;
     mbar_expect_tx(bar, tile_bytes + 160u);
     bulk_g2s(post, A.post + (unsigned long long)A.post_blk[blockIdx.z] * 40, 160u, bar);
-    if (p > 0) bulk_g2s(src, prv + S.off + (unsigned long long)tile * S.tile_words, tile_bytes, bar);
+    if (p > 0) {
+      const RowDev S = K.row[p - 1];
+      bulk_g2s(src, prv + S.off + (unsigned long long)tile * S.tile_words, tile_bytes, bar);
+    }
   }
   // ---- the rest of the geometry, while the copies fly: my crf state and predecessor column ----
   if (p == 0) {
@@ -399,14 +333,13 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
     src_g = (int)((idx << 1) | x);
     drop = x & R.dropmask;
   }
-  constexpr int ROWS = PD * LP;                                // [plane][slot] rows of one list's planes
+  constexpr int ROWS = (1 + NWD) * LP;                         // [plane][slot] rows of one list
   uint32_t *wown = own + warp * ROWS * 32;
-  const unsigned long long tile_d = R.off + (unsigned long long)(c >> 5) * R.tile_words;
-  const unsigned long long own_planes = tile_d + (unsigned long long)s * ROWS * 32 + (c & 31u);
-  const unsigned long long own_hist = tile_d + R.hist_off + ((unsigned long long)s * LP * 32 + (c & 31u)) * NWD;
+  const unsigned long long own_base = R.off + (unsigned long long)(c >> 5) * R.tile_words + (c & 31u) +
+                                      (unsigned long long)s * ROWS * 32;
   if (p > 0 && !one_bit) {
     // the warp's 8 conv states are consecutive: every (crf, plane, slot) row is 32 contiguous
-    // bytes in HBM -> 16-byte copies
+    // bytes in HBM -> 16-byte copies, 8 per lane, instead of 32 4-byte ones
     const uint32_t c0 = ((uint32_t)warp << (K.mem - 2)) | (tile * 8u);
     const unsigned long long wbase = R.off + (unsigned long long)(c0 >> 5) * R.tile_words + (c0 & 31u);
 #pragma unroll
@@ -419,7 +352,7 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
     }
   } else if (valid) {
 #pragma unroll
-    for (int r = 0; r < ROWS; r++) cp_async4(wown + r * 32 + pos, prv + own_planes + (unsigned long long)r * 32);
+    for (int r = 0; r < ROWS; r++) cp_async4(wown + r * 32 + pos, prv + own_base + (unsigned long long)r * 32);
   }
   cp_async_wait_all();
   __syncwarp();
@@ -427,32 +360,31 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   if (!valid) return;
 
   const uint32_t *mine = wown + pos;
-  uint32_t *dplanes = cur + own_planes;
+  uint32_t *dst = cur + own_base;
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
   if (p == 0) {  // VCC:706-713: stay edge only, slot 0 only
-    dplanes[0] = __float_as_uint(__uint_as_float(mine[0]) + wrow[s]);
+    dst[0] = __float_as_uint(__uint_as_float(mine[0]) + wrow[s]);
 #pragma unroll
     for (int l = 1; l < LP; l++)
-      if (l < L) dplanes[l * 32] = 0xff800000u;
+      if (l < L) dst[l * 32] = 0xff800000u;
     return;
   }
   const uint32_t *srcg = src + src_g;
-  const int list_w = PSRC * LP * TG;  // words between the crf lists of the staged planes
-  const uint32_t *gsrc = prv + S.off + (unsigned long long)tile * S.tile_words + S.hist_off + (uint32_t)src_g * nws;
   if (LP == 1) {
     // VCC:715-742: first strict maximum, own list first then predecessor crf ascending
     float best = neg_inf();
     int bk = -1;
     const float s0 = __uint_as_float(mine[0]) + wrow[s];
     if (s0 > best) { best = s0; bk = s; }
+    const int list_s = (1 + nws) * TG;
     const int k0 = s < 4 ? 0 : s - 4, k1 = s < 4 ? 7 : s - 4;
     for (int k = k0; k <= k1; k++) {
       if (k == s) continue;
-      const float sc = __uint_as_float(srcg[k * list_w]) + wrow[k];
+      const float sc = __uint_as_float(srcg[k * list_s]) + wrow[k];
       if (sc > best) { best = sc; bk = k; }
     }
-    dplanes[0] = __float_as_uint(best);
+    dst[0] = __float_as_uint(best);
     if (A.dec != nullptr) {
       // survivor mode: which predecessor won, 4 bits per state (crf of the source; == s means
       // "stayed"), the 8 states of a conv state packed into one word: flips low half, flops high
@@ -472,20 +404,17 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
         if ((lane & 1) == 0) *half = (unsigned short)v;
       }
     }
-    if (NWD > 0 && bk >= 0) {  // (metric -inf: hash and history are don't-care)
-      uint32_t *dh = cur + own_hist;
-      if (bk == s) {
-        dplanes[32] = mine[32];
+    if (NWD > 0) {
+      if (bk < 0 || bk == s) {  // (metric -inf: history is don't-care)
 #pragma unroll
-        for (int w = 0; w < NWD; w++) dh[w] = ldg_nc(prv + own_hist + w);
+        for (int w = 0; w < NWD; w++) dst[(1 + w) * 32] = mine[(1 + w) * 32];
       } else {
-        dplanes[32] = mix_hash(nws > 0 ? srcg[bk * list_w + TG] : 0u, drop);
         uint32_t prev = 0;
 #pragma unroll
         for (int w = 0; w < NWD; w++) {
           uint32_t old = 0;
-          if (w < nws) old = ldg_nc(gsrc + (bk * 32) * nws + w);
-          dh[w] = (old << R.shift) | (w == 0 ? drop : (prev >> (32 - R.shift)));
+          if (w < nws) old = srcg[bk * list_s + (1 + w) * TG];
+          dst[(1 + w) * 32] = (old << R.shift) | (w == 0 ? drop : (prev >> (32 - R.shift)));
           prev = old;
         }
       }
@@ -494,19 +423,22 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   }
   int n_acc;
   if (role == 0) {
-    ListView<LP, NWD, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), (uint32_t)list_w * 4u,
-                           gsrc, prv + own_hist, nws, (int)R.shift, s, drop};
-    n_acc = merge_lists<LP, NWD, 8>(dplanes, cur + own_hist, V, L);
+    ListView<LP, NWD, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), (uint32_t)(1 + nws) * LP * TG * 4u,
+                           nws, (int)R.shift, s, drop};
+    n_acc = merge_lists<LP, NWD, 8>(dst, V, L, true);
   } else {
-    ListView<LP, NWD, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), (uint32_t)list_w * 4u,
-                           gsrc, prv + own_hist, nws, (int)R.shift, s, drop};
-    n_acc = merge_lists<LP, NWD, 2>(dplanes, cur + own_hist, V, L);
+    ListView<LP, NWD, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), (uint32_t)(1 + nws) * LP * TG * 4u,
+                           nws, (int)R.shift, s, drop};
+    n_acc = merge_lists<LP, NWD, 2>(dst, V, L, true);
   }
-  if (n_acc < 0) {  // exact score tie between two list heads (libstdc++ heap order decides), or hash collision
-    exact_merge<LP>(prv, cur, post, &K, p, c, s, (int)(tile * TG + (uint32_t)src_g), drop);
+  if (n_acc < 0) {  // exact score tie between two list heads: libstdc++ heap order decides
+    uint32_t *mine_rw = wown + pos;
+    exact_merge<LP>(src, mine_rw, post, L, nws, NWD, TG, 32, R.shift, drop, s, src_g);
     atomicAdd(A.counters, 1ull);
+    for (int l = 0; l < L; l++)
+      for (int w = 0; w < 1 + NWD; w++) dst[(w * LP + l) * 32] = mine_rw[(w * LP + l) * 32];
   } else {
-    for (int l = n_acc; l < L; l++) dplanes[l * 32] = 0xff800000u;  // -inf; the rest of a dead slot is never read
+    for (int l = n_acc; l < L; l++) dst[l * 32] = 0xff800000u;  // -inf; history of a dead slot is never read
   }
 }
 
@@ -514,9 +446,8 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 inline size_t fast_smem_bytes(uint32_t LP, uint32_t nwd) {
-  // flip CTA: staged predecessor planes (8 lists) + own lists' planes; independent of the history width
-  const size_t planes = nwd > 0 ? 2 : 1;
-  return 256 + ((size_t)8 * planes * LP * 32 + planes * LP * kFastThreads) * 4;
+  // flip CTA, predecessors carrying as many words as the target row: tile + own (stay) lists
+  return 256 + ((size_t)8 * (1 + nwd) * LP * 32 + (size_t)(1 + nwd) * LP * kFastThreads) * 4;
 }
 
 #define LVA_FAST_LP_CASES(X) X(1) X(2) X(4) X(8) X(16)

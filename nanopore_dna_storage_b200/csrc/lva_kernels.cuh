@@ -130,95 +130,61 @@ __device__ __forceinline__ Target locate_target(const CodeDev &K, const RowDev &
 }
 
 // ---------------------------------------------------------------------------------------------
-// Addresses of one state's list inside a parity buffer (see lva_device.cuh for the layout)
-// ---------------------------------------------------------------------------------------------
-struct ListAddr {
-  unsigned long long planes;  // word index of (plane 0, slot 0)
-  unsigned long long hist;    // word index of (slot 0, word 0)
-  uint32_t nw, LP;
-  __device__ __forceinline__ unsigned long long metric(int j) const { return planes + (unsigned long long)j * 32; }
-  __device__ __forceinline__ unsigned long long hash(int j) const { return planes + (unsigned long long)(LP + j) * 32; }
-  __device__ __forceinline__ unsigned long long word(int j, int w) const { return hist + (unsigned long long)j * 32 * nw + w; }
-};
-__device__ __forceinline__ ListAddr list_addr(const RowDev &R, uint32_t LP, uint32_t c, uint32_t s) {
-  ListAddr A;
-  const unsigned long long tile = R.off + (unsigned long long)(c >> 5) * R.tile_words;
-  A.planes = tile + (unsigned long long)s * R.planes * LP * 32 + (c & 31u);
-  A.hist = tile + R.hist_off + ((unsigned long long)s * LP * 32 + (c & 31u)) * R.idwords;
-  A.nw = R.idwords;
-  A.LP = LP;
-  return A;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Exact list merge: bit-for-bit the reference's heap-driven k-way merge with de-duplication
-// (VCC:743-800) and its L=1 scan (VCC:715-742), ties included.  Reads the state's own previous
-// list and its predecessors' lists straight from the previous parity buffer and writes the new
-// list to the current one.  Used for every state in validation mode (LVA_FLAG_EXACT_ONLY, and
-// list sizes the fast path does not cover) and as the fallback of the fast path whenever two list
-// heads tie or a hash match fails verification.  Slow by design: one thread, global memory.
+// (VCC:743-800) and its L=1 scan (VCC:715-742), ties included.  Used for every state in
+// validation mode and as the fallback of the register fast path whenever two list heads tie.
+//
+//   src   : staged predecessor tile   [crf][plane][slot][TG]      (shared memory)
+//   mine  : this thread's own list    [plane][slot] stride NT     (shared memory; holds the STAY
+//           list of row p on entry, receives the new list on exit)
+//   post  : the 40 transition scores of step t
 // ---------------------------------------------------------------------------------------------
-// (plain struct with member functions: lambdas capturing by reference inside a __noinline__
-// device function miscompiled with nvcc 12.9)
-struct ExactCtx {
-  const uint32_t *prv;
-  uint32_t *cur;
-  ListAddr own;
-  RowDev S;
-  uint32_t LP, drop;
-  int src_c, s, nwd, nws, sh;
+// View of the lists one target state merges: its own (stay) list, copied to local memory, and
+// the predecessor lists inside the staged tile.
+template <int LP>
+struct MergeLists {
+  const uint32_t *src;   // staged tile base + src_g
+  int list_stride, plane_stride, tg;  // in words
+  int nws, nwd, sh, s;
+  uint32_t drop;
+  float st_sc[LP];
+  uint32_t st_id[LP * kMaxIdWords];
 
-  __device__ __forceinline__ ListAddr src_list(int k) const { return list_addr(S, LP, (uint32_t)src_c, (uint32_t)k); }
-  // candidate (list k, slot j): metric before the transition score
-  __device__ __forceinline__ float metric_of(int k, int j) const {
-    if (k == s) return __uint_as_float(prv[own.metric(j)]);
-    return __uint_as_float(prv[src_list(k).metric(j)]);
+  __device__ __forceinline__ float src_score(int k, int j) const {
+    return __uint_as_float(src[k * list_stride + j * tg]);
   }
-  // ... and the history words it would carry at the target
-  __device__ __forceinline__ void history_of(int k, int j, uint32_t *id) const {
+  __device__ __forceinline__ float score(int k, int j) const { return k == s ? st_sc[j] : src_score(k, j); }
+  // message history (nwd words) the candidate "entry j of list k" would carry at the target
+  __device__ __forceinline__ void history(int k, int j, uint32_t *id) const {
     if (k == s) {
-      for (int w = 0; w < nwd; w++) id[w] = prv[own.word(j, w)];
+      for (int w = 0; w < nwd; w++) id[w] = st_id[j * kMaxIdWords + w];
     } else {
-      const ListAddr a = src_list(k);
       uint32_t prev = 0;
       for (int w = 0; w < nwd; w++) {
-        const uint32_t old = w < nws ? prv[a.word(j, w)] : 0u;
+        uint32_t old = 0;
+        if (w < nws) old = src[k * list_stride + (1 + w) * plane_stride + j * tg];
         id[w] = (old << sh) | (w == 0 ? drop : (prev >> (32 - sh)));
         prev = old;
       }
     }
   }
-  __device__ __forceinline__ uint32_t hash_of(int k, int j) const {
-    if (nwd == 0) return 0u;
-    if (k == s) return prv[own.hash(j)];
-    const uint32_t h = nws > 0 ? prv[src_list(k).hash(j)] : 0u;
-    return mix_hash(h, drop);
-  }
-  __device__ __forceinline__ void emit(int l, float sc, int k, int j, const uint32_t *id) const {
-    cur[own.metric(l)] = __float_as_uint(sc);
-    if (nwd > 0) {
-      cur[own.hash(l)] = hash_of(k, j);
-      for (int w = 0; w < nwd; w++) cur[own.word(l, w)] = id[w];
-    }
-  }
 };
 
 template <int LP>
-__device__ __noinline__ void exact_merge(const uint32_t *prv, uint32_t *cur, const float *post,
-                                         const CodeDev *Kp, uint32_t p, uint32_t c, int s, int src_c,
-                                         uint32_t drop) {
-  const CodeDev &K = *Kp;
+__device__ __noinline__ void exact_merge(const uint32_t *src, uint32_t *mine, const float *post, int L,
+                                         int nws, int nwd, int TGv, int NT, int sh, uint32_t drop, int s,
+                                         int src_g) {
   const float NEG = neg_inf();
-  const int L = (int)K.L;
-  const RowDev R = K.row[p];
-  ExactCtx X;
-  X.prv = prv; X.cur = cur;
-  X.own = list_addr(R, LP, c, (uint32_t)s);
-  X.S = K.row[p - 1];
-  X.LP = LP; X.drop = drop; X.src_c = src_c; X.s = s;
-  X.nwd = R.idwords; X.nws = X.S.idwords; X.sh = R.shift;
-  const int nwd = X.nwd;
-  const ListAddr own = X.own;
+  MergeLists<LP> M;
+  M.src = src + (src_g >= 0 ? src_g : 0);
+  M.plane_stride = LP * TGv;
+  M.list_stride = (1 + nws) * M.plane_stride;
+  M.tg = TGv;
+  M.nws = nws; M.nwd = nwd; M.sh = sh; M.s = s; M.drop = drop;
+  for (int j = 0; j < L; j++) {
+    M.st_sc[j] = __uint_as_float(mine[j * NT]);
+    for (int w = 0; w < nwd; w++) M.st_id[j * kMaxIdWords + w] = mine[((1 + w) * LP + j) * NT];
+  }
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
   const int k_first = s < 4 ? 0 : s - 4, k_last = s < 4 ? 7 : s - 4;  // predecessor crf range
@@ -227,22 +193,21 @@ __device__ __noinline__ void exact_merge(const uint32_t *prv, uint32_t *cur, con
     float best = NEG;
     int bk = -1;
     {
-      const float sc = X.metric_of(s, 0) + wrow[s];
+      const float sc = M.st_sc[0] + wrow[s];
       if (sc > best) { best = sc; bk = s; }
     }
-    if (src_c >= 0) {
+    if (src_g >= 0) {
       for (int k = k_first; k <= k_last; k++) {
         if (k == s) continue;
-        const float sc = X.metric_of(k, 0) + wrow[k];
+        const float sc = M.src_score(k, 0) + wrow[k];
         if (sc > best) { best = sc; bk = k; }
       }
     }
-    cur[own.metric(0)] = __float_as_uint(best);
-    if (bk >= 0 && nwd > 0) {
+    mine[0] = __float_as_uint(best);
+    if (bk >= 0) {
       uint32_t id[kMaxIdWords];
-      X.history_of(bk, 0, id);
-      cur[own.hash(0)] = X.hash_of(bk, 0);
-      for (int w = 0; w < nwd; w++) cur[own.word(0, w)] = id[w];
+      M.history(bk, 0, id);
+      for (int w = 0; w < nwd; w++) mine[((1 + w) * LP) * NT] = id[w];
     }
     return;
   }
@@ -251,14 +216,11 @@ __device__ __noinline__ void exact_merge(const uint32_t *prv, uint32_t *cur, con
   uint32_t ht[8];
   HeapRef H{hs, ht};
   int n = 0;
-  {
-    const float sc = X.metric_of(s, 0);
-    if (sc != NEG) { hs[n] = sc + wrow[s]; ht[n] = (uint32_t)(s << 8); n++; }
-  }
-  if (src_c >= 0) {
+  if (M.st_sc[0] != NEG) { hs[n] = M.st_sc[0] + wrow[s]; ht[n] = (uint32_t)(s << 8); n++; }
+  if (src_g >= 0) {
     for (int k = k_first; k <= k_last; k++) {
       if (k == s) continue;
-      const float sc = X.metric_of(k, 0);
+      const float sc = M.src_score(k, 0);
       if (sc != NEG) { hs[n] = sc + wrow[k]; ht[n] = (uint32_t)(k << 8); n++; }
     }
   }
@@ -270,19 +232,20 @@ __device__ __noinline__ void exact_merge(const uint32_t *prv, uint32_t *cur, con
     const float sc = hs[n];
     const int k = (int)(ht[n] >> 8), j = (int)(ht[n] & 255u);
     uint32_t id[kMaxIdWords];
-    X.history_of(k, j, id);
+    M.history(k, j, id);
     bool dup = false;
-    for (int i = 0; i < l && !dup; i++) {  // compare with what this thread already wrote
+    for (int i = 0; i < l && !dup; i++) {
       bool same = true;
-      for (int w = 0; w < nwd; w++) same = same && (cur[own.word(i, w)] == id[w]);
+      for (int w = 0; w < nwd; w++) same = same && (mine[((1 + w) * LP + i) * NT] == id[w]);
       dup = same;
     }
     if (!dup) {
-      X.emit(l, sc, k, j, id);
+      mine[l * NT] = __float_as_uint(sc);
+      for (int w = 0; w < nwd; w++) mine[((1 + w) * LP + l) * NT] = id[w];
       l++;
     }
     if (j == L - 1) continue;
-    const float nxt = X.metric_of(k, j + 1);
+    const float nxt = M.score(k, j + 1);
     if (nxt != NEG) {
       hs[n] = nxt + wrow[k];
       ht[n] = (uint32_t)((k << 8) | (j + 1));
@@ -290,15 +253,19 @@ __device__ __noinline__ void exact_merge(const uint32_t *prv, uint32_t *cur, con
       heap_push(H, n);
     }
   }
-  for (; l < L; l++) cur[own.metric(l)] = __float_as_uint(NEG);
+  for (; l < L; l++) mine[l * NT] = __float_as_uint(NEG);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Generic step kernel: one thread per target state, everything through exact_merge.
+// Generic step kernel: every width (list slots LP, history words) is a run-time value and every
+// state goes through exact_merge.  Validation mode and fallback for shapes without a
+// specialised kernel.
+//   shared memory: [ post 40 f32 | pad ] [ src tile 8*(1+nws)*LP*TG ] [ own lists (1+nwd)*LP*NT ]
 // ---------------------------------------------------------------------------------------------
-template <int LP>
-__global__ void __launch_bounds__(256) lva_step_generic(const StepArgs A) {
-  constexpr int TG = 32;
+template <int LP, int TG>
+__global__ void __launch_bounds__(TG * 8) lva_step_generic(const StepArgs A) {
+  constexpr int NT = TG * 8;
+  extern __shared__ __align__(128) uint32_t smem[];
   const CodeDev &K = c_code[A.code_slot];
   const uint32_t a = A.band_a[blockIdx.z];
   uint32_t bend = a + A.dev2;
@@ -306,22 +273,53 @@ __global__ void __launch_bounds__(256) lva_step_generic(const StepArgs A) {
   if (bend > A.row_hi) bend = A.row_hi;  // a launch may be restricted to rows [row_lo, row_hi)
   const uint32_t p = (a > A.row_lo ? a : A.row_lo) + blockIdx.y;
   if (p >= bend) return;
+
   const RowDev R = K.row[p];
-  const Target T = locate_target<TG>(K, R, p, blockIdx.x, threadIdx.x);
-  if (!T.valid) return;
-  const uint32_t *prv = A.state + ((unsigned long long)blockIdx.z * 2 + (A.t & 1u)) * A.slot_words;
-  uint32_t *cur = A.state + ((unsigned long long)blockIdx.z * 2 + ((A.t + 1u) & 1u)) * A.slot_words;
-  const float *post = A.post + (unsigned long long)A.post_blk[blockIdx.z] * 40;
+  const int tid = threadIdx.x;
+  const uint32_t tile = blockIdx.x;
+  const Target T = locate_target<TG>(K, R, p, tile, tid);
+  if (!__syncthreads_or(T.valid)) return;
+
   const int L = (int)K.L;
-  if (p == 0) {  // VCC:706-713: only the stay edge, only slot 0
-    const ListAddr own = list_addr(R, LP, T.c, (uint32_t)T.s);
-    const int row = T.s >= 4 ? 4 : T.s;
-    cur[own.metric(0)] = __float_as_uint(__uint_as_float(prv[own.metric(0)]) + post[row * 8 + T.s]);
-    for (int l = 1; l < L; l++) cur[own.metric(l)] = __float_as_uint(neg_inf());
-    return;
+  const int nwd = R.idwords;
+  const int nws = p > 0 ? K.row[p - 1].idwords : 0;
+  float *post = reinterpret_cast<float *>(smem);
+  uint32_t *src = smem + 64;
+  uint32_t *own = src + 8 * (1 + nws) * LP * TG;
+
+  uint32_t *prv = A.state + ((unsigned long long)blockIdx.z * 2 + (A.t & 1u)) * A.slot_words;
+  uint32_t *cur = A.state + ((unsigned long long)blockIdx.z * 2 + ((A.t + 1u) & 1u)) * A.slot_words;
+
+  // ---- stage: posterior block, predecessor tile, own (stay) lists ----
+  if (tid < 10) cp_async16(post + tid * 4, A.post + (unsigned long long)A.post_blk[blockIdx.z] * 40 + tid * 4);
+  if (p > 0) {
+    const RowDev S = K.row[p - 1];
+    const uint32_t first = tile * TG;  // first predecessor conv state of this CTA
+    const uint32_t *g = prv + S.off + (unsigned long long)(first >> 5) * S.tile_words + (first & 31u);
+    const int lines = 8 * (1 + nws) * LP;      // each line: TG consecutive words
+    constexpr int CH = TG / 4;                 // 16-byte chunks per line
+    for (int i = tid; i < lines * CH; i += NT) {
+      const int line = i / CH, ch = i % CH;
+      cp_async16(src + line * TG + ch * 4, g + (unsigned long long)line * 32 + ch * 4);
+    }
   }
-  const int src_c = T.src_g >= 0 ? (int)(blockIdx.x * TG + (uint32_t)T.src_g) : -1;
-  exact_merge<LP>(prv, cur, post, &K, p, T.c, T.s, src_c, T.drop);
+  const unsigned long long own_base =
+      R.off + (unsigned long long)(T.c >> 5) * R.tile_words + (T.c & 31u) +
+      (unsigned long long)T.s * (1 + nwd) * LP * 32;
+  for (int i = 0; i < (1 + nwd) * LP; i++) cp_async4(own + i * NT + tid, prv + own_base + (unsigned long long)i * 32);
+  cp_async_wait_all();
+  __syncthreads();
+
+  if (!T.valid) return;
+  uint32_t *mine = own + tid;
+  if (p == 0) {  // VCC:706-713: only the stay edge, only slot 0
+    const int row = T.s >= 4 ? 4 : T.s;
+    mine[0] = __float_as_uint(__uint_as_float(mine[0]) + post[row * 8 + T.s]);
+    for (int l = 1; l < L; l++) mine[l * NT] = __float_as_uint(neg_inf());
+  } else {
+    exact_merge<LP>(src, mine, post, L, nws, nwd, TG, NT, R.shift, T.drop, T.s, T.src_g);
+  }
+  for (int i = 0; i < (1 + nwd) * LP; i++) cur[own_base + (unsigned long long)i * 32] = mine[i * NT];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -344,7 +342,8 @@ __global__ void lva_seed_start(uint32_t *state, unsigned long long slot_words, u
   const uint32_t slot = i >> 3, s = i & 7;
   const RowDev R = K.row[0];
   uint32_t *buf0 = state + (unsigned long long)slot * 2 * slot_words;
-  buf0[list_addr(R, K.LP, K.init, s).metric(0)] = 0u;  // 0.0f
+  buf0[R.off + (unsigned long long)(K.init >> 5) * R.tile_words +
+       ((unsigned long long)s * (1 + R.idwords) * K.LP) * 32 + (K.init & 31u)] = 0u;  // 0.0f
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -401,12 +400,13 @@ __global__ void lva_collect_final(const FinalArgs A) {
   const uint32_t slot = i / per_slot, e = i % per_slot, s = e / K.LP, j = e % K.LP;
   const ReadDev rd = A.reads[slot];
   const uint32_t *buf = A.state + ((unsigned long long)slot * 2 + (rd.T & 1u)) * A.slot_words;
-  const ListAddr la = list_addr(R, K.LP, K.fin, s);
-  const uint32_t planes = 1 + R.idwords;  // output record: metric, history words, CRC word
+  const unsigned long long base = R.off + (unsigned long long)(K.fin >> 5) * R.tile_words + (K.fin & 31u);
+  const uint32_t planes = 1 + R.idwords;
   uint32_t v[1 + kMaxIdWords];
-  v[0] = buf[la.metric((int)j)];
-  for (uint32_t w = 0; w < R.idwords; w++) v[1 + w] = buf[la.word((int)j, (int)w)];
-  for (uint32_t w = 0; w < planes; w++) A.out[(unsigned long long)i * (planes + 1) + w] = v[w];
+  for (uint32_t w = 0; w < planes; w++) {
+    v[w] = buf[base + ((unsigned long long)(s * planes + w) * K.LP + j) * 32];
+    A.out[(unsigned long long)i * (planes + 1) + w] = v[w];
+  }
   uint32_t crcw = 0;
   if (A.crc_pad >= 0 && v[0] != 0xff800000u) crcw = crc_word_of(K, v + 1, A.crc_pad);
   A.out[(unsigned long long)i * (planes + 1) + planes] = crcw;
@@ -434,7 +434,7 @@ __global__ void lva_traceback(const TraceArgs A) {
   {
     const RowDev R = K.row[p];
     for (int crf = 0; crf < 8; crf++) {  // first strict maximum == stable descending sort, first entry
-      const float sc = __uint_as_float(buf[list_addr(R, K.LP, c, (uint32_t)crf).metric(0)]);
+      const float sc = __uint_as_float(buf[R.off + (unsigned long long)(c >> 5) * R.tile_words + crf * 32 + (c & 31u)]);
       if (sc > best) { best = sc; s = crf; }
     }
   }

@@ -216,7 +216,6 @@ struct Final {
 bool g_stats_on = false;
 unsigned long long g_pop_hist[4][80];
 unsigned long long g_acc_hist[4][80];
-unsigned long long g_depth_hist[2][80];  // [0] deepest slot popped from a MOVE list per state, [1] from the STAY list
 
 }  // namespace
 
@@ -399,14 +398,12 @@ int lvo_decode(const lvo_params *prm, const float *post, uint32_t nblk, uint8_t 
             }
             std::make_heap(heap.begin(), heap.end());
             uint32_t l = 0;
-            uint32_t npop = 0, deep_move = 0, deep_stay = 0;
+            uint32_t npop = 0;
             while (!heap.empty() && l < L) {
               npop++;
               std::pop_heap(heap.begin(), heap.end());
               HeapItem h = heap.back();
               heap.pop_back();
-              if (h.psidx == 0) deep_stay = std::max(deep_stay, h.slot + 1);
-              else deep_move = std::max(deep_move, h.slot + 1);
               Msg mm = extend(prv_m[h.src * L + h.slot], e[h.psidx].shift, e[h.psidx].bits);
               if (std::find(cur_m + x * L, cur_m + x * L + l, mm) == cur_m + x * L + l) {
                 cur_m[x * L + l] = mm;
@@ -427,10 +424,6 @@ int lvo_decode(const lvo_params *prm, const float *post, uint32_t nblk, uint8_t 
               g_pop_hist[kind][npop < 79 ? npop : 79]++;
 #pragma omp atomic
               g_acc_hist[kind][l < 79 ? l : 79]++;
-#pragma omp atomic
-              g_depth_hist[0][deep_move]++;
-#pragma omp atomic
-              g_depth_hist[1][deep_stay]++;
             }
             for (; l < L; l++) cur_s[x * L + l] = NEG;
           }
@@ -469,10 +462,8 @@ void lvo_stats(int on, unsigned long long *pop_hist, unsigned long long *acc_his
     g_stats_on = on != 0;
     memset(g_pop_hist, 0, sizeof g_pop_hist);
     memset(g_acc_hist, 0, sizeof g_acc_hist);
-    memset(g_depth_hist, 0, sizeof g_depth_hist);
   }
 }
-void lvo_depth_stats(unsigned long long *out) { memcpy(out, g_depth_hist, sizeof g_depth_hist); }
 
 // --- libstdc++ heap primitives exposed for the device heap-emulation unit test ---------
 // op: 0 = make_heap, 1 = pop_heap (moves max to the back), 2 = push_heap (last element)

@@ -1,2 +1,3 @@
-mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:lva_step_fast -s 900 -c 3 -o gpurun_out/prof_h python bench.py --steps 1 --warmup 0 --reads-per-step 8 --slots 8 --no-cpu-baseline > gpurun_out/b2.log 2>&1
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full_size or survivor" 2>&1 | tail -3
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('C2', d['value'], d['config']['slots'], d['e2e']['value'], d['roofline']['frac'])"
+python bench.py --workload C3 --steps 1 --warmup 0 --no-cpu-baseline --reads-per-step 8 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('C3', d['value'], d['config']['slots'], d['e2e']['value'], d['roofline']['frac'], d['top1_correct_frac'])"
