@@ -79,59 +79,50 @@ struct ListView {
   }
 };
 
-// Accepted entries are remembered as (list, slot) descriptors, 8 bits each: a signature match is
-// verified by re-deriving the accepted entry's history from the staged lists.
+// Log of the accepted entries, kept as byte shift registers: byte k of register r describes the
+// (4r+k)-th most recent accept.  `pk` holds its (list << 4 | slot) descriptor -- a signature
+// match is verified by re-deriving that entry's history from the staged lists -- and `sig` a
+// one-byte signature of its history whose top bit is always set, so that the zero bytes of the
+// not yet filled positions never match.  Appending is two instructions per register; nothing is
+// indexed dynamically.
 template <int LP>
-struct Picks {
-  static_assert(LP <= 16, "descriptor words cover at most 16 slots");
-  uint32_t w0, w1, w2, w3;  // scalars on purpose: an indexed array would be demoted to local memory
-  __device__ __forceinline__ void clear() { w0 = w1 = w2 = w3 = 0; }
-  __device__ __forceinline__ void set(int l, uint32_t d) {
-    const uint32_t v = d << (8 * (l & 3));
-    const int q = l >> 2;
-    w0 |= q == 0 ? v : 0u;
-    if (LP > 4) w1 |= q == 1 ? v : 0u;
-    if (LP > 8) w2 |= q == 2 ? v : 0u;
-    if (LP > 12) w3 |= q == 3 ? v : 0u;
-  }
-  __device__ __forceinline__ uint32_t get(int l) const {
-    const int q = l >> 2;
-    uint32_t v = w0;
-    if (LP > 4) v = q == 1 ? w1 : v;
-    if (LP > 8) v = q == 2 ? w2 : v;
-    if (LP > 12) v = q == 3 ? w3 : v;
-    return (v >> (8 * (l & 3))) & 0xffu;
-  }
-};
-
-// One-byte signatures of the accepted entries, four per register.  match() returns a mask with
-// bit (8*(a&3) + (a>>2)) set for every accepted slot a whose signature MAY equal `sig8` (the
-// zero-byte test can flag a byte above a true match; callers verify), restricted to live slots.
-template <int LP>
-struct SigBytes {
+struct AcceptLog {
+  static_assert(LP <= 16, "four registers cover at most 16 slots");
   static constexpr int NR = (LP + 3) / 4;
-  uint32_t r0, r1, r2, r3, live;
-  __device__ __forceinline__ void clear() { r0 = r1 = r2 = r3 = live = 0; }
-  static __device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {
-    return ((x - 0x01010101u) & ~x & 0x80808080u) >> 7;
+  uint32_t sig[NR], pk[NR];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int r = 0; r < NR; r++) sig[r] = pk[r] = 0;
   }
+  static __device__ __forceinline__ uint32_t signature(uint32_t x) {  // byte sum of x, top bit forced
+    return ((x * 0x01010101u) >> 25) | 0x80u;
+  }
+  __device__ __forceinline__ void push(uint32_t sig8, uint32_t d) {
+#pragma unroll
+    for (int r = NR - 1; r > 0; r--) {
+      sig[r] = __funnelshift_l(sig[r - 1], sig[r], 8);
+      pk[r] = __funnelshift_l(pk[r - 1], pk[r], 8);
+    }
+    sig[0] = (sig[0] << 8) | sig8;
+    pk[0] = (pk[0] << 8) | d;
+  }
+  // bit (8k + r) is set when byte k of register r MAY equal sig8 (the zero-byte test can flag the
+  // byte above a true match; callers verify)
   __device__ __forceinline__ uint32_t match(uint32_t sig8) const {
     const uint32_t bc = sig8 * 0x01010101u;
-    uint32_t m = zero_bytes(r0 ^ bc);
-    if (NR > 1) m |= zero_bytes(r1 ^ bc) << 1;
-    if (NR > 2) m |= zero_bytes(r2 ^ bc) << 2;
-    if (NR > 3) m |= zero_bytes(r3 ^ bc) << 3;
-    return m & live;
+    uint32_t m = 0;
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const uint32_t x = sig[r] ^ bc;
+      m |= ((x - 0x01010101u) & ~x & 0x80808080u) >> (7 - r);
+    }
+    return m;
   }
-  static __device__ __forceinline__ int slot_of_bit(int pos) { return ((pos & 7) << 2) | (pos >> 3); }
-  __device__ __forceinline__ void insert(int l, uint32_t sig8) {
-    const uint32_t v = sig8 << (8 * (l & 3));
-    const int q = l >> 2;
-    r0 |= q == 0 ? v : 0u;
-    if (NR > 1) r1 |= q == 1 ? v : 0u;
-    if (NR > 2) r2 |= q == 2 ? v : 0u;
-    if (NR > 3) r3 |= q == 3 ? v : 0u;
-    live |= 1u << (8 * (l & 3) + q);
+  __device__ __forceinline__ uint32_t desc_at(int pos) const {  // pos: a bit index of match()
+    uint32_t v = pk[0];
+#pragma unroll
+    for (int r = 1; r < NR; r++) v = (pos & 3) == r ? pk[r] : v;
+    return (v >> (pos & 24)) & 0xffu;
   }
 };
 
@@ -176,10 +167,8 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
   int i;
   select_head<NL>(h, best, i);
   if (best == NEG) return 0;
-  Picks<LP> picks;
-  SigBytes<LP> sigs;
-  picks.clear();
-  sigs.clear();
+  AcceptLog<LP> log;
+  log.clear();
   uint32_t ptrs = 0;  // 4-bit read position per list
   int l = 0, prev_i = -1;
   float prev_best = __int_as_float(0x7f800000);  // +inf: never equals a metric
@@ -195,8 +184,7 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
     uint32_t csig = 0;
 #pragma unroll
     for (int w = 0; w < NWD; w++) csig ^= cand[w];
-    csig ^= csig >> 16;
-    csig = (csig ^ (csig >> 8)) & 0xffu;
+    csig = AcceptLog<LP>::signature(csig);
     // ---- chain B: advance the popped list and select the next candidate ----
     float nh = NEG;
     if (j + 1 < L) {
@@ -213,12 +201,11 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
     if (NWD == 0) {
       dup = l > 0;
     } else {
-      uint32_t m = sigs.match(csig);
+      uint32_t m = log.match(csig);
       dup = false;
       while (m != 0 && !dup) {
-        const int a = SigBytes<LP>::slot_of_bit(__ffs(m) - 1);
+        const uint32_t d = log.desc_at(__ffs(m) - 1);
         m &= m - 1u;
-        const uint32_t d = picks.get(a);
         uint32_t acc[NWD > 0 ? NWD : 1];
         V.history((int)(d >> 4), (int)(d & 15u), acc);
         uint32_t diff = 0;
@@ -232,8 +219,7 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
 #pragma unroll
       for (int w = 0; w < NWD; w++) dst[(1 + w) * LP * 32] = cand[w];
       dst += 32;
-      picks.set(l, (uint32_t)((i << 4) | j));
-      sigs.insert(l, csig);
+      log.push(csig, (uint32_t)((i << 4) | j));
       l++;
       if (l == L || NWD == 0) break;  // NWD == 0: every further candidate carries the same (empty) history
     }
