@@ -28,6 +28,7 @@ namespace lva {
 
 constexpr int kFastThreads = 128;
 
+
 // Everything a thread needs to address the lists it merges.  Staged lists -- the predecessor
 // tile and the warp's own (stay) lists -- share one shape: [plane][slot] rows of 32 words.
 //   NL = 8 (flip target s < 4): list i is predecessor crf i, except list s which is the state's
@@ -51,6 +52,9 @@ struct ListView {
   int nws, sh, s;
   uint32_t drop;
 
+  // keep the addresses in registers: left alone, the compiler rebuilds them from the thread's
+  // geometry inside the merge loop
+  __device__ __forceinline__ void pin() { asm volatile("" : "+r"(srcg), "+r"(mine), "+r"(wrow), "+r"(list_s)); }
   __device__ __forceinline__ int crf_of(int i) const { return NL == 8 ? i : (i == 0 ? s : s - 4); }
   __device__ __forceinline__ bool is_stay(int i) const { return NL == 8 ? i == s : i == 0; }
   __device__ __forceinline__ uint32_t base(int i) const {
@@ -106,22 +110,22 @@ struct AcceptLog {
     sig[0] = (sig[0] << 8) | sig8;
     pk[0] = (pk[0] << 8) | d;
   }
-  // bit (8k + r) is set when byte k of register r MAY equal sig8 (the zero-byte test can flag the
-  // byte above a true match; callers verify)
+  // bit (8k + 7 - r) is set when byte k of register r MAY equal sig8 (the zero-byte test can flag
+  // the byte above a true match; callers verify)
   __device__ __forceinline__ uint32_t match(uint32_t sig8) const {
     const uint32_t bc = sig8 * 0x01010101u;
     uint32_t m = 0;
 #pragma unroll
     for (int r = 0; r < NR; r++) {
       const uint32_t x = sig[r] ^ bc;
-      m |= ((x - 0x01010101u) & ~x & 0x80808080u) >> (7 - r);
+      m |= ((x - 0x01010101u) & ~x & 0x80808080u) >> r;
     }
     return m;
   }
   __device__ __forceinline__ uint32_t desc_at(int pos) const {  // pos: a bit index of match()
     uint32_t v = pk[0];
 #pragma unroll
-    for (int r = 1; r < NR; r++) v = (pos & 3) == r ? pk[r] : v;
+    for (int r = 1; r < NR; r++) v = (pos & 7) == 7 - r ? pk[r] : v;
     return (v >> (pos & 24)) & 0xffu;
   }
 };
@@ -152,9 +156,12 @@ __device__ __forceinline__ void select_head(const float (&h)[NL], float &best, i
 // depend on the accept/duplicate decision of the current one, so both chains sit in one loop
 // body and overlap.  An accepted candidate is stored to the new list in HBM right away: lanes
 // accept in lock step unless one of them met a duplicate (about once per state), so the stores
-// of a warp still land as complete sectors almost always.  Exact ties are detected lazily: two
-// consecutive pops with equal metric from different lists, or a head equal to the last popped
-// metric when the loop ends.
+// of a warp still land as complete sectors almost always.  Exact ties are detected lazily and only
+// where the heap order of the reference could show in the output: an entry accepted with the same
+// metric as the previously accepted one but from a different list, or a head equal to the last
+// accepted metric when the loop ends.  (A tie with a candidate that is dropped as a duplicate
+// cannot change the list: whichever copy of a message pops first, the same (message, metric)
+// pair is kept.)
 // Returns the number of accepted entries, or -1 on a tie (caller falls back to exact_merge and
 // overwrites whatever was stored).
 template <int LP, int NWD, int NL>
@@ -170,14 +177,11 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
   AcceptLog<LP> log;
   log.clear();
   uint32_t ptrs = 0;  // 4-bit read position per list
-  int l = 0, prev_i = -1;
-  float prev_best = __int_as_float(0x7f800000);  // +inf: never equals a metric
+  int l = 0, last_i = -1;
+  float last_acc = __int_as_float(0x7f800000);  // +inf: never equals a metric
   bool tie = false;
   while (true) {
     const int j = (ptrs >> (4 * i)) & 15;
-    tie = tie || (best == prev_best && i != prev_i);
-    prev_best = best;
-    prev_i = i;
     // ---- chain A: history and signature of the current candidate ----
     uint32_t cand[NWD > 0 ? NWD : 1];
     V.history(i, j, cand);
@@ -215,6 +219,9 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
       }
     }
     if (!dup) {
+      tie = tie || (best == last_acc && i != last_i);
+      last_acc = best;
+      last_i = i;
       dst[0] = __float_as_uint(best);  // dst walks the slots of the new list
 #pragma unroll
       for (int w = 0; w < NWD; w++) dst[(1 + w) * LP * 32] = cand[w];
@@ -228,7 +235,7 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
     i = ni;
   }
 #pragma unroll
-  for (int i2 = 0; i2 < NL; i2++) tie = tie || (h[i2] == prev_best);
+  for (int i2 = 0; i2 < NL; i2++) tie = tie || (h[i2] == last_acc);
   return tie ? -1 : l;
 }
 
@@ -411,10 +418,12 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   if (role == 0) {
     ListView<LP, NWD, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), (uint32_t)(1 + nws) * LP * TG * 4u,
                            nws, (int)R.shift, s, drop};
+    V.pin();
     n_acc = merge_lists<LP, NWD, 8>(dst, V, L, true);
   } else {
     ListView<LP, NWD, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), (uint32_t)(1 + nws) * LP * TG * 4u,
                            nws, (int)R.shift, s, drop};
+    V.pin();
     n_acc = merge_lists<LP, NWD, 2>(dst, V, L, true);
   }
   if (n_acc < 0) {  // exact score tie between two list heads: libstdc++ heap order decides
