@@ -1,20 +1,24 @@
 // Fast path of the trellis step, specialised on list slots (LP) and on the number of
 // message-history words of the target row (NWD).
 //
-// Geometry: one HBM tile of 32 predecessor conv states per CTA, 128 threads, and a ROLE per CTA
-// (blockIdx.x & 1): role 0 computes the 128 flip targets fed by the tile, role 1 the 128 flop
-// targets.  Flip targets merge 8 lists, flop targets 2, so giving them separate CTAs lets the
-// short ones retire and free their SM slot instead of idling beside the long ones.
-//   * the predecessor tile is ONE contiguous chunk (flop CTAs need only its first half, the
-//     four flip lists) -> a single TMA bulk copy (cp.async.bulk, SASS UBLKCP) into shared
-//     memory, completion on an mbarrier; the step's 40 transition scores ride the same barrier;
+// Geometry: one HBM tile of 32 predecessor conv states per CTA.  The tile feeds 128 flip targets
+// (8-list merges) and 128 flop targets (2-list merges) of row p:
+//   LVA_MERGED_ROLES = 1 (default): one 256-thread CTA does both, warps 0-3 the flip targets and
+//     warps 4-7 the flop targets, from ONE staged copy of the tile (measured +3 % over the split:
+//     20 % fewer tile bytes through L2 and less shared-memory residency per unit of work);
+//   LVA_MERGED_ROLES = 0: a 128-thread CTA per role (blockIdx.x & 1), the flop CTA staging only the
+//     four flip lists (first half of the tile).
+//   * the predecessor tile is ONE contiguous chunk -> a single TMA bulk copy (cp.async.bulk, SASS
+//     UBLKCP) into shared memory, completion on an mbarrier; the step's 40 transition scores ride
+//     the same barrier;
 //   * each thread owns one target state (p, c, s); the 32 lanes of a warp read 32 DIFFERENT
 //     predecessor conv states, which in the tile-transposed layout are 32 different banks ->
 //     no bank conflicts whatever the (crf, slot, plane) pattern;
 //   * the new list is built by a flat k-way merge (one candidate popped per trip by every lane)
-//     with de-duplication on the message history: a one-word XOR signature per accepted entry
-//     is kept in registers, signature matches (rare: ~1 per state) are verified word by word;
-//     accepted entries are kept as (list, slot) descriptors and materialised when stored;
+//     with de-duplication on the message history: a one-byte signature and a (list, slot)
+//     descriptor per accepted entry are kept in byte shift registers, signature matches (about one
+//     per state) are verified word by word against the staged lists; an accepted entry is stored
+//     to the new list right away;
 //   * states that no conv transition can produce (two of the four bases of every conv state on
 //     rows entered by a one-bit step) are never touched: they keep their initial -inf;
 //   * whenever two list heads tie exactly for the maximum the thread re-runs that state through
@@ -26,7 +30,10 @@
 
 namespace lva {
 
-constexpr int kFastThreads = 128;
+#ifndef LVA_MERGED_ROLES
+#define LVA_MERGED_ROLES 1
+#endif
+constexpr int kFastThreads = LVA_MERGED_ROLES ? 256 : 128;
 
 
 // Everything a thread needs to address the lists it merges.  Staged lists -- the predecessor
@@ -253,42 +260,51 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
 
   const RowDev R = K.row[p];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if LVA_MERGED_ROLES
+  const uint32_t tile = blockIdx.x;
+  const int cta_role = tid >> 7;  // (p == 0 only) threads 0..127 flip, 128..255 flop
+  const int warp4 = warp & 3, tid7 = tid & 127;
+#else
   const int cta_role = blockIdx.x & 1;
   const uint32_t tile = blockIdx.x >> 1;
+  const int warp4 = warp, tid7 = tid;
+#endif
   // Rows entered by a one-bit step (puncturing block 0) can produce only two of the four bases
   // per conv state: the other two flip states and their flop states have no predecessor, are
   // never reached and keep the -inf they were initialised with.  For such rows ONE CTA per tile
   // handles the 64 live flip targets (warps 0-1) and the 64 live flop targets (warps 2-3).
   const bool one_bit = p > 0 && R.shift == 1;
+#if !LVA_MERGED_ROLES
   if (one_bit && cta_role == 1) return;
+#endif
   // ---- which target state is mine (cheap part first: the tile copy is issued before the rest) ----
   uint32_t c, drop = 0, run, idx, lo;
   int s, src_g = -1, role, pos;  // pos: my word inside the warp's 32-word list rows
   if (p == 0) {
     role = cta_role;
-    run = tid >> 6; idx = (tid >> 2) & 15u; lo = tile * 16u + idx;
+    run = tid7 >> 6; idx = (tid7 >> 2) & 15u; lo = tile * 16u + idx;
     c = (run << (K.mem - 1)) | lo;
     pos = lane;
   } else if (!one_bit) {
-    role = cta_role;  // 0: the 128 flip targets of the tile, 1: the 128 flop targets
-    run = warp; idx = lane >> 2; lo = tile * 8u + idx;  // a warp = 8 consecutive conv states x 4 bases
+    role = LVA_MERGED_ROLES ? (warp >> 2) : cta_role;  // 0: the 128 flip targets of the tile, 1: the 128 flop targets
+    run = warp4; idx = lane >> 2; lo = tile * 8u + idx;  // a warp = 8 consecutive conv states x 4 bases
     c = (run << (K.mem - 2)) | lo;
     pos = (int)((lane & 3u) * 8u + idx);
   } else {
-    role = warp >> 1;
+    role = (warp >> 1) & 1;
     const uint32_t tg = (tid & 63) >> 1;
     run = tg >> 4; idx = tg & 15u; lo = tile * 16u + idx;
     c = (run << (K.mem - 1)) | lo;
     pos = lane;
   }
-  const bool valid = (c & R.vmask) == R.vval;
+  const bool valid = (c & R.vmask) == R.vval && !(LVA_MERGED_ROLES && one_bit && warp >= 4);
 
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);          // bytes 0..7
   float *post = reinterpret_cast<float *>(smem + 4);           // bytes 16..175
   uint32_t *src = smem + 64;                                   // byte 256
   const int nws = p > 0 ? K.row[p - 1].idwords : 0;
   // flop-only CTAs read just the flip lists 0..3 = the first half of the tile
-  const int n_src_lists = (p > 0 && !one_bit && role == 1) ? 4 : 8;
+  const int n_src_lists = (!LVA_MERGED_ROLES && p > 0 && !one_bit && role == 1) ? 4 : 8;
   uint32_t *own = src + n_src_lists * (1 + nws) * LP * TG;     // stay lists, per warp [plane][slot][32]
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -333,7 +349,7 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   if (p > 0 && !one_bit) {
     // the warp's 8 conv states are consecutive: every (crf, plane, slot) row is 32 contiguous
     // bytes in HBM -> 16-byte copies, 8 per lane, instead of 32 4-byte ones
-    const uint32_t c0 = ((uint32_t)warp << (K.mem - 2)) | (tile * 8u);
+    const uint32_t c0 = ((uint32_t)warp4 << (K.mem - 2)) | (tile * 8u);
     const unsigned long long wbase = R.off + (unsigned long long)(c0 >> 5) * R.tile_words + (c0 & 31u);
 #pragma unroll
     for (int k = 0; k < (ROWS * 8 + 31) / 32; k++) {
@@ -486,7 +502,7 @@ inline cudaError_t fast_launch_step(uint32_t LP, cudaStream_t st, StepArgs a, co
     while (q < hi && k.idwords[q] == nw) q++;
     a.row_lo = p;
     a.row_hi = q;
-    dim3 grid(2 * (k.nconv / 32), q - p, active);  // x: (tile, role)
+    dim3 grid((LVA_MERGED_ROLES ? 1 : 2) * (k.nconv / 32), q - p, active);  // x: (tile, role)
     cudaError_t e = cudaErrorInvalidValue;
 #define Y(lp, nwc) \
   if (LP == lp && nw == nwc) e = fast_launch_one<lp, nwc>(st, grid, a);
