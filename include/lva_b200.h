@@ -150,6 +150,33 @@ typedef struct lva_timing {
 } lva_timing;
 int lva_get_timing(const lva_handle *h, lva_timing *out);
 
+/* ---- posterior trimming -------------------------------------------------
+ * Replaces, for a batch of reads, helper.find_barcode_pos_in_post (helper.py:157-209) called for the
+ * forward barcodes and for their reverse complements, and the orientation / size rule of the driver
+ * (generate_decoded_lists.py:68-83).  helper.truncate_post_file (helper.py:211-224) needs no
+ * counterpart: pass [out_start, out_end + 1) as the read's block range to lva_decode_batch.
+ *   basecalls / base_offsets   concatenated basecalls (ACGTN bytes), read i = [base_offsets[i], base_offsets[i+1])
+ *   trans / trans_offsets      concatenated flappie .trans tables (flappie.c:278-282: one block index per base)
+ *   start_barcode, end_barcode as given to the driver; the RC pair is rc(end), rc(start) (generate_decoded_lists.py:33-34)
+ *   min_blocks                 mem_conv + msg_len + 1 (generate_decoded_lists.py:76)
+ * Outputs per read (host, caller-owned): out_start / out_end = first / last payload block (inclusive;
+ * -1 on failure), out_rc = 1 when the reverse-complement barcodes match better, out_status = LVA_TRIM_*,
+ * out_dist (may be NULL) = [n_reads][4] edit distances start/end forward, start/end rc (0xFFFFFFFF = the
+ * reference's inf).  Returns LVA_OK or LVA_ERR_BAD_ARG / _NO_DEVICE / _OOM / _CUDA.  No CPU path. */
+#define LVA_TRIM_MAX_BARCODE 64
+enum {
+  LVA_TRIM_OK = 0,
+  LVA_TRIM_TOO_SHORT = 1,      /* helper.py:177-179 "Too short read" */
+  LVA_TRIM_BARCODE_ORDER = 2,  /* helper.py:207-209 "Barcode removal failure" (end before start) */
+  LVA_TRIM_TOO_FEW_BLOCKS = 3, /* generate_decoded_lists.py:76 "Failure in barcode removing." */
+  LVA_TRIM_NO_WINDOW = 4       /* no window to search / .trans shorter than the basecall: the reference raises */
+};
+int lva_trim_batch(int32_t device, const char *basecalls, const uint64_t *base_offsets,
+                   const uint32_t *trans, const uint64_t *trans_offsets, uint32_t n_reads,
+                   const char *start_barcode, const char *end_barcode, uint32_t min_blocks,
+                   int32_t *out_start, int32_t *out_end, int32_t *out_rc, int32_t *out_status,
+                   uint32_t *out_dist);
+
 const char *lva_version(void);
 
 #ifdef __cplusplus
