@@ -456,9 +456,9 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
-inline size_t fast_smem_bytes(uint32_t LP, uint32_t nwd) {
-  // flip CTA, predecessors carrying as many words as the target row: tile + own (stay) lists
-  return 256 + ((size_t)8 * (1 + nwd) * LP * 32 + (size_t)(1 + nwd) * LP * kFastThreads) * 4;
+inline size_t fast_smem_bytes(uint32_t LP, uint32_t nwd, uint32_t threads = kFastThreads) {
+  // predecessors carrying as many words as the target row: tile + own (stay) lists of every thread
+  return 256 + ((size_t)8 * (1 + nwd) * LP * 32 + (size_t)(1 + nwd) * LP * threads) * 4;
 }
 
 #define LVA_FAST_LP_CASES(X) X(1) X(2) X(4) X(8) X(16)
@@ -487,8 +487,8 @@ inline cudaError_t fast_prepare(uint32_t LP, uint32_t nw_last) {
 }
 
 template <int LP, int NWD>
-inline cudaError_t fast_launch_one(cudaStream_t st, dim3 grid, const StepArgs &a) {
-  lva_step_fast<LP, NWD><<<grid, kFastThreads, fast_smem_bytes(LP, NWD), st>>>(a);
+inline cudaError_t fast_launch_one(cudaStream_t st, dim3 grid, uint32_t threads, const StepArgs &a) {
+  lva_step_fast<LP, NWD><<<grid, threads, fast_smem_bytes(LP, NWD, threads), st>>>(a);
   return cudaGetLastError();
 }
 
@@ -503,9 +503,17 @@ inline cudaError_t fast_launch_step(uint32_t LP, cudaStream_t st, StepArgs a, co
     a.row_lo = p;
     a.row_hi = q;
     dim3 grid((LVA_MERGED_ROLES ? 1 : 2) * (k.nconv / 32), q - p, active);  // x: (tile, role)
+    // rows entered by a one-bit step have 64 + 64 live targets per tile (warps 0-3): when a launch
+    // holds nothing else (every row of a rate-1/2 code), half the merged CTA would sit idle
+    uint32_t threads = kFastThreads;
+    if (LVA_MERGED_ROLES && p > 0) {
+      bool all_one_bit = true;
+      for (uint32_t r = p; r < q; r++) all_one_bit = all_one_bit && k.shift[r] == 1;
+      if (all_one_bit) threads = 128;
+    }
     cudaError_t e = cudaErrorInvalidValue;
 #define Y(lp, nwc) \
-  if (LP == lp && nw == nwc) e = fast_launch_one<lp, nwc>(st, grid, a);
+  if (LP == lp && nw == nwc) e = fast_launch_one<lp, nwc>(st, grid, threads, a);
 #define X(lp) LVA_FAST_NW_CASES(Y, lp)
     LVA_FAST_LP_CASES(X)
 #undef X
