@@ -153,3 +153,34 @@ def test_full_size_headline_config_properties():
         exact = dec.decode([r.post for r in noisy])
     for (b1, s1), (b2, s2) in zip(fast, exact):
         assert np.array_equal(b1, b2) and np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
+
+
+@pytest.mark.parametrize("mem,rate,msg_len,L,marker,period,rc", [
+    (6, 1, 40, 4, "110", 9, False), (6, 5, 40, 8, "01", 7, True), (8, 3, 40, 4, "1011", 12, False),
+    (8, 5, 40, 8, "1", 5, True),
+])
+def test_sync_markers_match_oracle(oracle, mem, rate, msg_len, L, marker, period, rc):
+    """--sync-marker / --sync-period pin message bits (is_valid_state, VCC:944-978): same lists and
+    metrics as the oracle on posteriors of messages that do NOT carry the marker (hard reads)."""
+    w = synth.Workload("sync", mem, rate, msg_len, L, 20, sub=0.01, dele=0.01, ins=0.005, seed=7100 + mem + rate)
+    reads = [synth.make_read(w, i) for i in range(4)]
+    for exact_only in (True, False):
+        with ListDecoder(mem, rate, msg_len, L, 20, rc=rc, sync_marker=marker, sync_period=period,
+                         exact_only=exact_only) as dec:
+            got = dec.decode([r.post for r in reads])
+        for r, (bits, scores) in zip(reads, got):
+            st, obits, oscores = oracle.oracle_decode(r.post, mem, rate, msg_len, L, 20, rc, marker, period)
+            assert st == 0
+            assert bits.shape == obits.shape and np.array_equal(bits, obits), (mem, rate, marker, exact_only)
+            assert np.array_equal(scores.view(np.uint32), oscores.view(np.uint32))
+
+
+@pytest.mark.parametrize("mem,rate,msg_len,L", [(6, 1, 248, 2), (8, 5, 242, 4)])
+def test_longest_messages_use_all_history_words(oracle, mem, rate, msg_len, L):
+    """msg_len + mem_conv close to the 256-bit limit of the reference's bitset (VCC:604-605): rows
+    carrying 7 and 8 history words per entry (the widest step-kernel instantiations)."""
+    from nanopore_dna_storage_b200.decoder import code_tables
+    assert max(code_tables(mem, rate, msg_len)["history_words"]) == 8
+    w = synth.Workload("long", mem, rate, msg_len, L, 20, sub=0.004, dele=0.0085, ins=0.0005, seed=7200 + mem)
+    _compare(oracle, w, 2, exact_only=False, tag=f"long m{mem} r{rate}")
+    _compare(oracle, w, 1, exact_only=True, tag=f"long exact m{mem} r{rate}")
