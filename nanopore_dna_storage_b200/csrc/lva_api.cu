@@ -314,7 +314,16 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
     const uint64_t ctas_per_read = std::max<uint64_t>(1, band_rows * 2 * (k.nconv / 32));
     slots = (uint32_t)std::min<uint64_t>(kMaxSlots, std::max<uint64_t>(64, (64ull * 4 * h->sm_count + ctas_per_read - 1) / ctas_per_read));
   }
+  size_t per_slot_all = per_slot;
+  if (h->survivor) {
+    // list size 1: a step of one read is a few microseconds of work -> as many reads in flight as fit
+    // next to their decision arrays (T x band rows x conv states words; T estimated at 5 blocks per row)
+    const uint64_t band_rows = std::min<uint64_t>(std::max<uint64_t>(2ull * h->max_dev, 1), k.nrows);
+    per_slot_all += (size_t)(5ull * k.nrows * band_rows * k.nconv * 4ull);
+    if (!params->max_slots) slots = kMaxSlots;
+  }
   if (slots > (uint32_t)kMaxSlots) slots = kMaxSlots;
+  if ((size_t)slots * per_slot_all > budget) slots = (uint32_t)std::max<size_t>(1, budget / per_slot_all);
   if ((size_t)slots * per_slot > budget) slots = (uint32_t)(budget / per_slot);
   if (slots == 0) { lva_destroy(h); return fail(LVA_ERR_OOM, "not enough device memory for one read"); }
   h->n_slots = slots;
@@ -524,7 +533,13 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
         a.band_a[s] = band[rd[s].band_off + t];
         a.post_blk[s] = (uint32_t)(rd[s].post_block + t);
       }
-      if (h->use_fast) {
+      if (h->use_fast && h->survivor && getenv("LVA_NO_L1_KERNEL") == nullptr) {
+        L1Args l1{a.state, a.slot_words, a.post, a.dec, a.dec_slot_words, (const ReadDev *)h->d_reads.p,
+                  (const uint16_t *)h->d_band.p, a.dec_rows, t, a.dev2, a.code_slot};
+        cudaError_t e = l1_launch_step(h->stream, l1, k, active);
+        if (e != cudaSuccess) { h->err = std::string("L=1 step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
+        h->timing.step_launches++;
+      } else if (h->use_fast) {
         cudaError_t e = fast_launch_step(h->LP, h->stream, a, k, lo, hi, active, &h->timing.step_launches);
         if (e != cudaSuccess) { h->err = std::string("fast step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
       } else {

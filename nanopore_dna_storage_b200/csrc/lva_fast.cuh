@@ -454,6 +454,108 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// lva_step_l1: the whole step for list size 1 in survivor mode (metrics only, VCC:715-742), the
+// reference tool's default.  A list-size-1 state is one float: staging tiles through shared memory
+// and one thread per product state (lva_step_fast<1,0>) spend ten times more instructions on
+// geometry than on the update.  Here one thread owns a conv state (p, c): it reads the 8 metrics of
+// the state itself and of each predecessor conv state straight from L2 (the band state of every
+// read in flight fits there), updates the up to 8 crf states in the reference's order (stay first,
+// then predecessor crf ascending, first strict maximum) and writes the 8 four-bit decisions as ONE
+// 32-bit word, coalesced over c.  grid = (band rows x conv states / 256, 1, reads); the per-read
+// control data (band start, posterior block) comes from the tables the traceback uses.
+// ---------------------------------------------------------------------------------------------
+struct L1Args {  // small on purpose: 800+ launches per batch, the launch itself is what costs
+  uint32_t *state;
+  unsigned long long slot_words;
+  const float *post;
+  uint32_t *dec;
+  unsigned long long dec_slot_words;
+  const ReadDev *reads;   // per slot: first posterior block, T, offset of its band table
+  const uint16_t *band;   // band starts a_t of every read in flight (VCC:677-678)
+  uint32_t dec_rows, t, dev2, code_slot;
+};
+
+__global__ void __launch_bounds__(256) lva_step_l1(const L1Args A) {
+  __shared__ float post[40];
+  const CodeDev &K = c_code[A.code_slot];
+  const uint32_t z = blockIdx.z;
+  const ReadDev rd = A.reads[z];
+  const uint32_t a = A.band[rd.band_off + A.t];
+  uint32_t bend = a + A.dev2;
+  if (bend > K.nrows) bend = K.nrows;
+  if (threadIdx.x < 40) post[threadIdx.x] = A.post[(rd.post_block + A.t) * 40 + threadIdx.x];
+  __syncthreads();
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;  // (band row, conv state), conv state fastest
+  const uint32_t p = a + idx / K.nconv, c = idx & (K.nconv - 1u);
+  if (p >= bend) return;
+  const RowDev R = K.row[p];
+  if ((c & R.vmask) != R.vval) return;
+  const uint32_t *prv = A.state + ((unsigned long long)z * 2 + (A.t & 1u)) * A.slot_words;
+  uint32_t *cur = A.state + ((unsigned long long)z * 2 + ((A.t + 1u) & 1u)) * A.slot_words;
+  const unsigned long long own = R.off + (unsigned long long)(c >> 5) * R.tile_words + (c & 31u);  // + s * 32
+  float mine[8];
+#pragma unroll
+  for (int s = 0; s < 8; s++) mine[s] = __uint_as_float(prv[own + s * 32]);
+  if (p == 0) {  // VCC:706-713: stay edge only
+#pragma unroll
+    for (int s = 0; s < 8; s++) cur[own + s * 32] = __float_as_uint(mine[s] + post[(s >= 4 ? 4 : s) * 8 + s]);
+    return;
+  }
+  const RowDev S = K.row[p - 1];
+  const uint32_t m = K.mem, sh = R.shift;
+  const uint32_t run = c >> (m - sh), lo = c & ((1u << (m - sh)) - 1u);
+  const uint32_t e0 = sh == 2 ? emitted_base(K, R.block, lo << 2, run & 1u, run >> 1) : emitted_base(K, 0, lo << 1, run, 0);
+  uint32_t word = 0;
+  const int nb = sh == 2 ? 4 : 2;  // producible bases of this conv state
+  for (int q = 0; q < nb; q++) {
+    uint32_t b, cp;  // the base, and the predecessor conv state that emits it on the way to c
+    if (sh == 2) {
+      b = (uint32_t)q;
+      cp = (lo << 2) | ((R.inv_lin >> (2 * (b ^ e0))) & 3u);
+    } else {
+      b = e0 ^ (q ? R.lin1 : 0u);
+      cp = (lo << 1) | (uint32_t)q;
+    }
+    const unsigned long long srcb = S.off + (unsigned long long)(cp >> 5) * S.tile_words + (cp & 31u);
+    float src[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) src[k] = __uint_as_float(prv[srcb + k * 32]);
+    {  // flip state b: stay, then every other crf state of the predecessor
+      float best = neg_inf();
+      int bk = -1;
+      const float s0 = mine[b] + post[b * 8 + b];
+      if (s0 > best) { best = s0; bk = (int)b; }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (k == (int)b) continue;
+        const float sc = src[k] + post[b * 8 + k];
+        if (sc > best) { best = sc; bk = k; }
+      }
+      cur[own + b * 32] = __float_as_uint(best);
+      word |= ((uint32_t)(bk < 0 ? (int)b : bk) & 7u) << (4 * b);
+    }
+    {  // flop state b+4: stay, then the flip state b of the predecessor
+      const uint32_t s = b + 4;
+      float best = neg_inf();
+      int bk = -1;
+      const float s0 = mine[s] + post[32 + s];
+      if (s0 > best) { best = s0; bk = (int)s; }
+      const float sc = src[b] + post[32 + b];
+      if (sc > best) { best = sc; bk = (int)b; }
+      cur[own + s * 32] = __float_as_uint(best);
+      word |= ((uint32_t)(bk < 0 ? (int)s : bk) & 7u) << (4 * s);
+    }
+  }
+  A.dec[(unsigned long long)z * A.dec_slot_words + ((unsigned long long)A.t * A.dec_rows + (p - a)) * K.nconv + c] = word;
+}
+
+inline cudaError_t l1_launch_step(cudaStream_t st, const L1Args &a, const CodeSpec &k, uint32_t active) {
+  const uint32_t rows = a.dev2 < k.nrows ? a.dev2 : k.nrows;  // band rows of one read at one step
+  lva_step_l1<<<dim3((rows * k.nconv + 255) / 256, 1, active), 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 inline size_t fast_smem_bytes(uint32_t LP, uint32_t nwd, uint32_t threads = kFastThreads) {
