@@ -516,6 +516,8 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     a.dec = h->survivor ? (uint32_t *)h->d_dec.p : nullptr;
     a.dec_slot_words = dec_slot_words;
     a.dec_rows = dec_rows;
+    // developer switch for A/B runs: list size 1 through the tile-staging kernel lva_step_fast<1,0>
+    static const bool no_l1_kernel = getenv("LVA_NO_L1_KERNEL") != nullptr;
     const uint32_t Tmax = Ts[0];
     uint32_t active = ns;
     for (uint32_t t = 0; t < Tmax; t++) {
@@ -533,7 +535,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
         a.band_a[s] = band[rd[s].band_off + t];
         a.post_blk[s] = (uint32_t)(rd[s].post_block + t);
       }
-      if (h->use_fast && h->survivor && getenv("LVA_NO_L1_KERNEL") == nullptr) {
+      if (h->use_fast && h->survivor && !no_l1_kernel) {
         L1Args l1{a.state, a.slot_words, a.post, a.dec, a.dec_slot_words, (const ReadDev *)h->d_reads.p,
                   (const uint16_t *)h->d_band.p, a.dec_rows, t, a.dev2, a.code_slot};
         cudaError_t e = l1_launch_step(h->stream, l1, k, active);
