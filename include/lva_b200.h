@@ -177,6 +177,20 @@ int lva_trim_batch(int32_t device, const char *basecalls, const uint64_t *base_o
                    int32_t *out_start, int32_t *out_end, int32_t *out_rc, int32_t *out_status,
                    uint32_t *out_dist);
 
+/* ---- flip-flop transition posteriors ------------------------------------
+ * Replaces transpost_crf_flipflop(trans, return_log = true) (flappie/src/decode.c:377-497, with
+ * logsumexpf util.h:188-190 and log_row_normalise_inplace flappie_matrix.c:450-467) for a batch of
+ * reads: from the CRF transition weights of the flappie network to the log-posteriors the decoder
+ * reads.  trans and out_post: concatenated blocks of 40 floats in the .post order (flappie's
+ * column-major 40 x nblk matrix is exactly that), read i = blocks [block_offsets[i], block_offsets[i+1]).
+ * Sums are folded in the reference's order; results differ from the CPU only by the last-bit
+ * behaviour of expf / log1pf.  The _device variant takes and fills device memory of `device`, so
+ * the posteriors can go straight into lva_decode_batch_device.  Returns LVA_OK or an LVA_ERR_*. */
+int lva_posteriors_batch(int32_t device, const float *trans, const uint64_t *block_offsets, uint32_t n_reads,
+                         float *out_post);
+int lva_posteriors_batch_device(int32_t device, const float *trans_dev, const uint64_t *block_offsets,
+                                uint32_t n_reads, float *out_post_dev);
+
 const char *lva_version(void);
 
 #ifdef __cplusplus

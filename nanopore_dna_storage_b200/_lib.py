@@ -15,7 +15,7 @@ LVA_DEFAULT_DEVIATION = 0xFFFFFFFF
 LVA_FLAG_EXACT_ONLY = 1
 
 EXPORTS = ["lva_create", "lva_destroy", "lva_last_error", "lva_decode_batch", "lva_decode_batch_device", "lva_decode_batch_crc",
-           "lva_trim_batch", "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_version"]
+           "lva_trim_batch", "lva_posteriors_batch", "lva_posteriors_batch_device", "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_version"]
 
 
 class LvaParams(C.Structure):
@@ -75,6 +75,9 @@ def lib() -> C.CDLL:
     L.lva_trim_batch.restype = C.c_int
     L.lva_trim_batch.argtypes = [C.c_int32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
                                  C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for fn in (L.lva_posteriors_batch, L.lva_posteriors_batch_device):
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.lva_encode.restype = C.c_int
     L.lva_encode.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                              C.POINTER(C.c_uint32)]
