@@ -107,6 +107,15 @@ def ncu_traffic():
         return None
 
 
+def ncu_pipes():
+    """Issue / pipe utilisation of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pipes.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def cpu_reference_run(w: synth.Workload, reads, threads: int):
     """Time the reference's own decoder (oracle/_ref, unmodified sources compiled in place) on a
     bounded sample; falls back to the oracle port if the compiled reference is absent."""
@@ -268,6 +277,10 @@ def main():
                                           f"{tr['algorithmic_bytes_same_launch']} B algorithmic for that launch") if tr else None},
             "clocks": clocks,
         }
+        pipes = ncu_pipes()
+        if pipes and args.workload == "C2":
+            line["roofline"]["issue"] = {k: pipes[k] for k in ("issue_active_pct", "alu_pipe_pct", "fma_pipe_pct",
+                                                               "lsu_pipe_pct", "source") if k in pipes}
         if world == 1 and not args.no_cpu_baseline:
             cpu_reads = synth.make_reads(w, max(1, args.cpu_reads), start=10_000_000)
             kind, rps, dt = cpu_reference_run(w, cpu_reads, threads)
