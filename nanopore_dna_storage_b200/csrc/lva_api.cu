@@ -71,6 +71,8 @@ struct lva_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
   DevBuf d_state, d_reads, d_band, d_post, d_final, d_counters;
+  CUtensorMap own_maps[kMaxIdWords + 1];  // per history width: view of d_state for the own-list TMA copies
+  bool own_tma = false;
   PinnedBuf h_stage, h_final, h_post;
   std::string err;
   lva_timing timing{};
@@ -182,6 +184,36 @@ struct FinalEntry {
 extern "C" {
 
 const char *lva_version(void) { return "lva_b200 0.1 (sm_100a)"; }
+
+// Tensor maps for the own-list copies of lva_step_fast: the state buffer as a 3-D tensor
+// (32 conv columns | 8 crf lists, ROWS*128 bytes apart | 128-byte rows), box {8, 4, ROWS}; ROWS depends on
+// the history width of the row class, hence one map per width.  cuTensorMapEncodeTiled comes from the
+// driver through the runtime's entry-point query (no link against libcuda).  Failure -> cp.async path.
+static bool make_own_maps(lva_handle *h) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess)
+    return false;
+  const unsigned long long total_rows = (unsigned long long)h->n_slots * 2ull * h->slot_words / 32ull;
+  if (total_rows == 0 || total_rows > 0xffffffffull) return false;
+  for (uint32_t nw = 0; nw <= h->nw_last; nw++) {
+    const cuuint32_t rows = (1u + nw) * h->LP;
+    if (rows > 256) return false;
+    const cuuint64_t dims[3] = {32, 8, total_rows};
+    const cuuint64_t strides[2] = {(cuuint64_t)rows * 128ull, 128ull};  // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {8, 4, rows};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (((encode_fn)fn)(&h->own_maps[nw], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, h->d_state.p, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
 
 lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t err_len) {
   auto fail = [&](int st, const std::string &msg) -> lva_handle * {
@@ -334,6 +366,7 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
     return fail(LVA_ERR_OOM, "allocation failed");
   }
   cudaMemset(h->d_counters.p, 0, 64);
+  h->own_tma = h->use_fast && h->LP > 1 && getenv("LVA_NO_OWN_TMA") == nullptr && make_own_maps(h);
   if (status) *status = LVA_OK;
   return h;
 }
@@ -516,6 +549,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     a.dec = h->survivor ? (uint32_t *)h->d_dec.p : nullptr;
     a.dec_slot_words = dec_slot_words;
     a.dec_rows = dec_rows;
+    a.own_tma = h->own_tma ? 1u : 0u;
     // developer switch for A/B runs: list size 1 through the tile-staging kernel lva_step_fast<1,0>
     static const bool no_l1_kernel = getenv("LVA_NO_L1_KERNEL") != nullptr;
     const uint32_t Tmax = Ts[0];
@@ -542,7 +576,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
         if (e != cudaSuccess) { h->err = std::string("L=1 step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
         h->timing.step_launches++;
       } else if (h->use_fast) {
-        cudaError_t e = fast_launch_step(h->LP, h->stream, a, k, lo, hi, active, &h->timing.step_launches);
+        cudaError_t e = fast_launch_step(h->LP, h->stream, a, k, lo, hi, active, &h->timing.step_launches, h->own_maps);
         if (e != cudaSuccess) { h->err = std::string("fast step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
       } else {
         a.row_lo = 0;

@@ -62,6 +62,7 @@ struct StepArgs {
   uint32_t *dec;                  // nullptr unless the handle runs in survivor mode
   unsigned long long dec_slot_words;
   uint32_t dec_rows;              // band rows per step in the decision array
+  uint32_t own_tma;               // 1: the own lists of two-bit rows come through the tensor map passed beside this struct
   uint32_t post_blk[kMaxSlots];   // per active slot: index of the posterior block of this step
   uint16_t band_a[kMaxSlots];     // per active slot: first in-band row of this step (VCC:677-678)
 };

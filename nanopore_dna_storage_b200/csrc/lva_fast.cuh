@@ -247,7 +247,7 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
 }
 
 template <int LP, int NWD>
-__global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) {
+__global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, const __grid_constant__ CUtensorMap own_map) {
   constexpr int NT = kFastThreads, TG = 32;
   extern __shared__ __align__(128) uint32_t smem[];
   const CodeDev &K = c_code[A.code_slot];
@@ -317,13 +317,30 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
   uint32_t *cur = A.state + ((unsigned long long)blockIdx.z * 2 + ((A.t + 1u) & 1u)) * A.slot_words;
 
   // ---- stage ----
+  constexpr int ROWS = (1 + NWD) * LP;                         // [plane][slot] rows of one list
+  // Own lists of a two-bit row: warp w needs, of target tile tt(w), the 8 conv columns 8*(tile&3).. of
+  // the four crf lists of its role -- a 3-D box {8 columns, 4 crf, ROWS rows} of the state buffer seen
+  // as (32 columns, crf stride ROWS*128 B, 128-byte rows), which lands in shared memory as
+  // [row][crf][8] = exactly the [row][pos] layout the merge reads.  One TMA copy per warp instead of
+  // ROWS*8/32 16-byte cp.async per lane (which cost the LSU two L2 requests per 32-byte sector).
+  const bool own_by_tma = A.own_tma != 0 && p > 0 && !one_bit;
   if (tid == 0) {
     const uint32_t tile_bytes = p > 0 ? (uint32_t)n_src_lists * (1 + nws) * LP * TG * 4u : 0u;
-    mbar_expect_tx(bar, tile_bytes + 160u);
+    const uint32_t nwarps = blockDim.x >> 5;
+    mbar_expect_tx(bar, tile_bytes + 160u + (own_by_tma ? nwarps * (uint32_t)ROWS * 32u * 4u : 0u));
     bulk_g2s(post, A.post + (unsigned long long)A.post_blk[blockIdx.z] * 40, 160u, bar);
     if (p > 0) {
       const RowDev S = K.row[p - 1];
       bulk_g2s(src, prv + S.off + (unsigned long long)tile * S.tile_words, tile_bytes, bar);
+    }
+    if (own_by_tma) {
+      const unsigned long long buf = ((unsigned long long)blockIdx.z * 2 + (A.t & 1u)) * A.slot_words + R.off;
+      for (uint32_t w = 0; w < nwarps; w++) {
+        const uint32_t w4 = LVA_MERGED_ROLES ? (w & 3u) : w, wrole = LVA_MERGED_ROLES ? (w >> 2) : (uint32_t)cta_role;
+        const uint32_t cw = (w4 << (K.mem - 2)) | (tile * 8u);  // first conv state of the warp
+        const unsigned long long row128 = (buf + (unsigned long long)(cw >> 5) * R.tile_words) >> 5;
+        tensor3d_g2s(own + w * ROWS * 32, &own_map, (int)(cw & 31u), (int)(4u * wrole), (int)row128, bar);
+      }
     }
   }
   // ---- the rest of the geometry, while the copies fly: my crf state and predecessor column ----
@@ -342,11 +359,12 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A) 
     src_g = (int)((idx << 1) | x);
     drop = x & R.dropmask;
   }
-  constexpr int ROWS = (1 + NWD) * LP;                         // [plane][slot] rows of one list
   uint32_t *wown = own + warp * ROWS * 32;
   const unsigned long long own_base = R.off + (unsigned long long)(c >> 5) * R.tile_words + (c & 31u) +
                                       (unsigned long long)s * ROWS * 32;
-  if (p > 0 && !one_bit) {
+  if (own_by_tma) {
+    // (issued above by thread 0)
+  } else if (p > 0 && !one_bit) {
     // the warp's 8 conv states are consecutive: every (crf, plane, slot) row is 32 contiguous
     // bytes in HBM -> 16-byte copies, 8 per lane, instead of 32 4-byte ones
     const uint32_t c0 = ((uint32_t)warp4 << (K.mem - 2)) | (tile * 8u);
@@ -589,14 +607,14 @@ inline cudaError_t fast_prepare(uint32_t LP, uint32_t nw_last) {
 }
 
 template <int LP, int NWD>
-inline cudaError_t fast_launch_one(cudaStream_t st, dim3 grid, uint32_t threads, const StepArgs &a) {
-  lva_step_fast<LP, NWD><<<grid, threads, fast_smem_bytes(LP, NWD, threads), st>>>(a);
+inline cudaError_t fast_launch_one(cudaStream_t st, dim3 grid, uint32_t threads, const StepArgs &a, const CUtensorMap &own_map) {
+  lva_step_fast<LP, NWD><<<grid, threads, fast_smem_bytes(LP, NWD, threads), st>>>(a, own_map);
   return cudaGetLastError();
 }
 
 // One time step: one launch per distinct history width among rows [lo, hi).
 inline cudaError_t fast_launch_step(uint32_t LP, cudaStream_t st, StepArgs a, const CodeSpec &k, uint32_t lo,
-                                    uint32_t hi, uint32_t active, uint64_t *n_launches) {
+                                    uint32_t hi, uint32_t active, uint64_t *n_launches, const CUtensorMap *own_maps) {
   uint32_t p = lo;
   while (p < hi) {
     const uint32_t nw = k.idwords[p];
@@ -615,7 +633,7 @@ inline cudaError_t fast_launch_step(uint32_t LP, cudaStream_t st, StepArgs a, co
     }
     cudaError_t e = cudaErrorInvalidValue;
 #define Y(lp, nwc) \
-  if (LP == lp && nw == nwc) e = fast_launch_one<lp, nwc>(st, grid, threads, a);
+  if (LP == lp && nw == nwc) e = fast_launch_one<lp, nwc>(st, grid, threads, a, own_maps[nwc]);
 #define X(lp) LVA_FAST_NW_CASES(Y, lp)
     LVA_FAST_LP_CASES(X)
 #undef X

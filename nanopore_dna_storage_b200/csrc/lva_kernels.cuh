@@ -7,6 +7,7 @@
 // states of row p that those predecessors reach -- the butterfly of Appendix B in SURVEY.md.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "heap_order.cuh"
@@ -48,6 +49,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(phase)
+      : "memory");
+}
+// 3-D tiled copy global -> shared through the TMA unit (SASS: UTMALDG), completion on an mbarrier.
+// `map` must live in kernel-parameter space (const __grid_constant__ CUtensorMap).
+__device__ __forceinline__ void tensor3d_g2s(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
 // 1-D bulk copy global -> shared through the TMA unit (SASS: UBLKCP), completion on an mbarrier
