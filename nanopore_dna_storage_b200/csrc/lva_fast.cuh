@@ -229,9 +229,10 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NWD
       tie = tie || (best == last_acc && i != last_i);
       last_acc = best;
       last_i = i;
-      dst[0] = __float_as_uint(best);  // dst walks the slots of the new list
+      __stcs(dst, __float_as_uint(best));  // dst walks the slots of the new list; streaming stores: the new
+                                           // list is not read again before 2-3 GB of other traffic went by
 #pragma unroll
-      for (int w = 0; w < NWD; w++) dst[(1 + w) * LP * 32] = cand[w];
+      for (int w = 0; w < NWD; w++) __stcs(dst + (1 + w) * LP * 32, cand[w]);
       dst += 32;
       log.push(csig, (uint32_t)((i << 4) | j));
       l++;
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
     for (int l = 0; l < L; l++)
       for (int w = 0; w < 1 + NWD; w++) dst[(w * LP + l) * 32] = mine_rw[(w * LP + l) * 32];
   } else {
-    for (int l = n_acc; l < L; l++) dst[l * 32] = 0xff800000u;  // -inf; history of a dead slot is never read
+    for (int l = n_acc; l < L; l++) __stcs(dst + l * 32, 0xff800000u);  // -inf; history of a dead slot is never read
   }
 }
 
