@@ -155,3 +155,26 @@ def test_sharding_plan_balances_blocks():
         loads = [sum(lens[i] for i in s) for s in shards]
         assert max(loads) - min(loads) <= max(lens)
     assert plan([], 4) == [[], [], [], []]
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing in the package may import, link or execute it, and the
+    trimming / posterior entry points have no CPU path either (they fail without a device)."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "nanopore_dna_storage_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle/_|liblva_oracle|libvcc_ref|libflipflop", re.M)
+    for dirpath, _, files in os.walk(root):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not pat.search(text), f"{f} refers to the oracle"
+    import torch
+    if not torch.cuda.is_available():
+        from nanopore_dna_storage_b200 import posteriors, trim
+        with pytest.raises(RuntimeError):
+            posteriors.transpost_crf_flipflop([np.zeros((3, 40), np.float32)])
+        with pytest.raises(RuntimeError):
+            trim.find_barcodes_and_orientation(["ACGT" * 30], [list(range(1, 121))], "ACGTACGT", "TTGGCCAA", 6, 40)
