@@ -90,6 +90,15 @@ int lva_decode_batch_device(lva_handle *h, const float *post_dev, const uint64_t
                             uint32_t n_reads, uint8_t *out_bits, float *out_scores,
                             uint32_t *out_counts, int32_t *out_status);
 
+/* Same as lva_decode_batch / lva_decode_batch_device for reads that are arbitrary block ranges of one
+ * posterior array: read i owns blocks [block_starts[i], block_ends[i]) (ranges may leave gaps or
+ * overlap).  This is what helper.truncate_post_file (helper.py:211-224) does with a file copy: pass
+ * the [start, end + 1) ranges lva_trim_batch found and the untrimmed posteriors stay where they are
+ * (post_on_device != 0: `post` is device memory, e.g. the output of lva_posteriors_batch_device). */
+int lva_decode_ranges(lva_handle *h, const float *post, int32_t post_on_device, const uint64_t *block_starts,
+                      const uint64_t *block_ends, uint32_t n_reads, uint8_t *out_bits, float *out_scores,
+                      uint32_t *out_counts, int32_t *out_status);
+
 /* lva_decode_batch plus the check the reference's drivers run on every list afterwards
  * (helper.decode_list_CRC_index, helper.py:371-388; framing helper.py:257-264), computed on the GPU
  * for all candidates: strip the pad bit (pad != 0), left-pad to whole bytes, CRC-8 (poly 0x07, init 0)
@@ -147,6 +156,10 @@ typedef struct lva_timing {
   uint64_t step_launches;   /* of which trellis step kernels */
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t exact_fallbacks; /* states resolved by the exact heap-order path after a score tie */
+  uint64_t chain_inserts;   /* distinct (chain id, chunk) keys interned by the call (all reads) */
+  uint64_t chain_keys_max;  /* ... the most any one read needed */
+  uint64_t chain_table_slots; /* slots of one read's chain table */
+  uint64_t table_regrows;   /* times the call was repeated with larger chain tables */
 } lva_timing;
 int lva_get_timing(const lva_handle *h, lva_timing *out);
 

@@ -14,7 +14,7 @@ CLI_PATH = os.path.join(HERE, "_build", "viterbi_nanopore.out")
 LVA_DEFAULT_DEVIATION = 0xFFFFFFFF
 LVA_FLAG_EXACT_ONLY = 1
 
-EXPORTS = ["lva_create", "lva_destroy", "lva_last_error", "lva_decode_batch", "lva_decode_batch_device", "lva_decode_batch_crc",
+EXPORTS = ["lva_create", "lva_destroy", "lva_last_error", "lva_decode_batch", "lva_decode_batch_device", "lva_decode_batch_crc", "lva_decode_ranges",
            "lva_trim_batch", "lva_posteriors_batch", "lva_posteriors_batch_device", "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_version"]
 
 
@@ -39,7 +39,9 @@ class LvaWork(C.Structure):
 class LvaTiming(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("kernel_ms", C.c_float), ("h2d_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("launches", C.c_uint64), ("step_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("exact_fallbacks", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("exact_fallbacks", C.c_uint64),
+                ("chain_inserts", C.c_uint64), ("chain_keys_max", C.c_uint64),
+                ("chain_table_slots", C.c_uint64), ("table_regrows", C.c_uint64)]
 
 
 def build(verbose: bool = False) -> None:
@@ -68,6 +70,9 @@ def lib() -> C.CDLL:
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                        C.c_void_p, C.c_void_p]
+    L.lva_decode_ranges.restype = C.c_int
+    L.lva_decode_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
     L.lva_decode_batch_crc.restype = C.c_int
     L.lva_decode_batch_crc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -127,6 +127,21 @@ int build_code_spec(CodeSpec &k, uint32_t mem, uint32_t rate, uint32_t msg_len, 
     k.idwords[p] = (uint8_t)((hist + 31) / 32);
     const uint32_t real = std::min<uint32_t>(k.shift[p], hist);
     k.dropmask[p] = (uint8_t)((1u << real) - 1u);
+    k.app[p] = (uint8_t)real;
+  }
+  // chunking of the message history: a move into row p appends app[p] bits to the partial chunk
+  // of row p-1; when they no longer fit 32 bits, row p-1 is a boundary row (its partial chunk is
+  // complete and gets interned) and row p starts a new chunk with the appended bits only
+  k.nchunks = 0;
+  for (uint32_t p = 1; p < k.nrows; p++) {
+    if ((uint32_t)k.plen[p - 1] + k.app[p] > 32u) {
+      k.boundary[p - 1] = 1;
+      k.chunk_len[k.nchunks++] = k.plen[p - 1];
+      k.plen[p] = k.app[p];
+    } else {
+      k.plen[p] = (uint8_t)(k.plen[p - 1] + k.app[p]);
+    }
+    k.chunk_of[p] = (uint8_t)k.nchunks;
   }
   return kCodeOk;
 }

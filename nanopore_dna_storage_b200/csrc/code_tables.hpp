@@ -46,8 +46,18 @@ struct CodeSpec {
   uint8_t shift[kMaxRows] = {0};    // message bits consumed entering row p (0 for p = 0)
   uint32_t vmask[kMaxRows] = {0};   // conv state c is reachable at row p iff (c & vmask) == vval
   uint32_t vval[kMaxRows] = {0};
-  uint8_t idwords[kMaxRows] = {0};  // 32-bit words of message history kept per list entry
+  uint8_t idwords[kMaxRows] = {0};  // 32-bit words of message history (what the reference's bitset would hold)
   uint8_t dropmask[kMaxRows] = {0}; // which of the `shift` bits leaving the register are message bits
+
+  // Message identity of a list entry: the message bits that already left the conv
+  // register are kept in ABSOLUTE coordinates (message bit b at string position b) as a chain of
+  // completed chunks of <= 32 bits, named by one canonical 32-bit id, plus the partial chunk.
+  uint8_t app[kMaxRows] = {0};      // message bits appended to the partial chunk by a move INTO row p (0..2)
+  uint8_t plen[kMaxRows] = {0};     // bits in the partial chunk at row p (<= 32)
+  uint8_t boundary[kMaxRows] = {0}; // 1: the partial chunk of row p is complete; a move out of it starts a new one
+  uint8_t chunk_of[kMaxRows] = {0}; // number of completed chunks behind an entry of row p
+  uint32_t nchunks = 0;             // completed chunks behind an entry of the last row
+  uint8_t chunk_len[16] = {0};      // bits of completed chunk k
 };
 
 int build_code_spec(CodeSpec &k, uint32_t mem, uint32_t rate, uint32_t msg_len, bool rc,

@@ -64,30 +64,28 @@ struct lva_handle {
   CodeSpec code;
   CodeDev dev_code{};
   int device = 0, code_slot = -1;
-  uint32_t L = 1, LP = 1, max_dev = 0, nw_last = 0;
+  uint32_t L = 1, LP = 1, max_dev = 0;
   uint32_t n_slots = 0;
-  unsigned long long slot_words = 0;
+  // state geometry (lva_device.cuh): window rows, words per piece / row / parity buffer
+  uint32_t window = 0, piece_words = 0, row_words = 0, nid_ring = 1;
+  unsigned long long parity_words = 0, nid_parity_words = 0;
+  uint32_t tab_slots = 0;      // interning table slots per read in flight (power of two)
+  unsigned long long slot_words = 0;  // survivor mode: words of one parity buffer
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
-  DevBuf d_state, d_reads, d_band, d_post, d_final, d_counters;
-  CUtensorMap own_maps[kMaxIdWords + 1];  // per history width: view of d_state for the own-list TMA copies
-  bool own_tma = false;
+  DevBuf d_state, d_nid, d_tab, d_reads, d_band, d_post, d_final, d_counters;
+  FastMaps maps{};
   PinnedBuf h_stage, h_final, h_post;
   std::string err;
   lva_timing timing{};
-  // CRC request of the call in progress (lva_decode_batch_crc)
-  int crc_pad = -1;
-  uint32_t crc_num_oligos = 0;
-  uint8_t *crc_ok_out = nullptr;
-  uint16_t *crc_index_out = nullptr;
-  int32_t *crc_choice_out = nullptr;
-  bool survivor = false;     // list size 1: metrics + 4-bit decisions + traceback instead of histories
+  bool survivor = false;     // list size 1: metrics + 4-bit decisions + traceback instead of list entries
   DevBuf d_dec, d_trace;
   PinnedBuf h_trace;
   int gen_tg = 32;           // tile width of the generic kernel
   size_t gen_smem = 0;
   bool use_fast = false;
+  bool all_one_bit = false;
 };
 
 namespace {
@@ -152,7 +150,7 @@ cudaError_t prep_generic(size_t smem) {
 }
 
 #define LVA_GENERIC_CASES(X) \
-  X(1, 32) X(2, 32) X(4, 32) X(8, 32) X(16, 32) X(16, 16) X(32, 16) X(32, 8) X(64, 8) X(64, 4)
+  X(1, 32) X(2, 32) X(4, 32) X(8, 32) X(16, 32) X(16, 16) X(32, 16) X(32, 8) X(64, 8)
 
 cudaError_t generic_prepare(const lva_handle *h) {
 #define X(lp, tg) \
@@ -169,9 +167,11 @@ cudaError_t generic_launch(const lva_handle *h, dim3 grid, const StepArgs &a) {
   return cudaErrorInvalidValue;
 }
 
-size_t generic_smem_bytes(uint32_t LP, uint32_t tg, uint32_t nw) {
-  return 256 + ((size_t)8 * (1 + nw) * LP * tg + (size_t)(1 + nw) * LP * tg * 8) * 4;
+size_t generic_smem_bytes(uint32_t LP, uint32_t tg) {
+  return 256 + ((size_t)24 * LP * tg + (size_t)3 * LP * tg * 8) * 4;
 }
+
+constexpr size_t kCounterBytes = (8 + kMaxSlots) * sizeof(unsigned long long);  // [0] fallbacks [1] overflow [8+z] keys of slot z
 
 struct FinalEntry {
   float score;
@@ -179,41 +179,75 @@ struct FinalEntry {
   uint32_t crcw;
 };
 
-}  // namespace
+// CRC-8 / index request of one call (lva_decode_batch_crc)
+struct CrcReq {
+  int pad = -1;  // -1: none
+  uint32_t num_oligos = 0;
+  uint8_t *ok_out = nullptr;
+  uint16_t *index_out = nullptr;
+  int32_t *choice_out = nullptr;
+};
 
-extern "C" {
+__global__ void lva_seed_start_l1(uint32_t *state, unsigned long long slot_words, uint32_t code_slot, uint32_t n_slots) {
+  const CodeDev &K = c_code[code_slot];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots * 8) return;
+  state[(unsigned long long)(i >> 3) * 2 * slot_words + l1_word(K, 0, K.init, i & 7)] = 0u;  // 0.0f
+}
 
-const char *lva_version(void) { return "lva_b200 0.1 (sm_100a)"; }
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// Tensor maps for the own-list copies of lva_step_fast: the state buffer as a 3-D tensor
-// (32 conv columns | 8 crf lists, ROWS*128 bytes apart | 128-byte rows), box {8, 4, ROWS}; ROWS depends on
-// the history width of the row class, hence one map per width.  cuTensorMapEncodeTiled comes from the
-// driver through the runtime's entry-point query (no link against libcuda).  Failure -> cp.async path.
-static bool make_own_maps(lva_handle *h) {
-  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// Tensor maps of lva_step_fast (lva_fast.cuh): the state buffer seen as
+//   src: (8 conv columns | pieces, piece_bytes apart | 24*LP rows of 32 bytes), box {8, 4 pieces, 8*LP rows = one plane}
+//   own: (8 columns | 8 crf lists | LP slots | 3 planes | pieces), box {8, 4 crf, LP, 3, 1 piece}
+// and the nid ring like src with one plane per piece.  cuTensorMapEncodeTiled comes from the
+// driver through the runtime's entry-point query (no link against libcuda).
+std::string make_maps(lva_handle *h) {
   void *fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
       qres != cudaDriverEntryPointSuccess)
-    return false;
-  const unsigned long long total_rows = (unsigned long long)h->n_slots * 2ull * h->slot_words / 32ull;
-  if (total_rows == 0 || total_rows > 0xffffffffull) return false;
-  for (uint32_t nw = 0; nw <= h->nw_last; nw++) {
-    const cuuint32_t rows = (1u + nw) * h->LP;
-    if (rows > 256) return false;
-    const cuuint64_t dims[3] = {32, 8, total_rows};
-    const cuuint64_t strides[2] = {(cuuint64_t)rows * 128ull, 128ull};  // bytes, dims 1 and 2
-    const cuuint32_t box[3] = {8, 4, rows};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (((encode_fn)fn)(&h->own_maps[nw], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, h->d_state.p, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return false;
+    return "cuTensorMapEncodeTiled entry point not available";
+  const cuuint64_t ppr = h->code.nconv / 8;
+  const cuuint64_t pieces = (cuuint64_t)h->n_slots * 2ull * h->window * ppr;
+  const cuuint64_t nid_pieces = (cuuint64_t)h->n_slots * 2ull * h->nid_ring * ppr;
+  const cuuint64_t piece_bytes = (cuuint64_t)h->piece_words * 4ull, LP = h->LP;
+  if (pieces > 0x7fffffffull || nid_pieces > 0x7fffffffull) return "state buffer too large for 32-bit tensor coordinates";
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  auto enc = [&](CUtensorMap *m, cuuint32_t rank, void *base, const cuuint64_t *dims, const cuuint64_t *strides,
+                 const cuuint32_t *box) {
+    return ((tmap_encode_fn)fn)(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, rank, base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  {
+    const cuuint64_t dims[3] = {8, pieces, 24 * LP}, strides[2] = {piece_bytes, 32};
+    const cuuint32_t box[3] = {8, 4, (cuuint32_t)(8 * LP)};
+    CUresult r = enc(&h->maps.src, 3, h->d_state.p, dims, strides, box);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled(src) failed: " + std::to_string((int)r);
   }
-  return true;
+  {
+    const cuuint64_t dims[5] = {8, 8, LP, 3, pieces}, strides[4] = {LP * 32, 32, 8 * LP * 32, piece_bytes};
+    const cuuint32_t box[5] = {8, 4, (cuuint32_t)LP, 3, 1};
+    CUresult r = enc(&h->maps.own, 5, h->d_state.p, dims, strides, box);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled(own) failed: " + std::to_string((int)r);
+  }
+  {
+    const cuuint64_t dims[3] = {8, nid_pieces, 8 * LP}, strides[2] = {8 * LP * 32, 32};
+    const cuuint32_t box[3] = {8, 4, (cuuint32_t)(8 * LP)};
+    CUresult r = enc(&h->maps.nid, 3, h->d_nid.p, dims, strides, box);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled(nid) failed: " + std::to_string((int)r);
+  }
+  return "";
 }
+
+}  // namespace
+
+extern "C" {
+
+const char *lva_version(void) { return "lva_b200 0.2 (sm_100a)"; }
 
 lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t err_len) {
   auto fail = [&](int st, const std::string &msg) -> lva_handle * {
@@ -250,14 +284,11 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   h->LP = next_pow2(h->L);
   h->max_dev = params->max_deviation == LVA_DEFAULT_DEVIATION ? params->msg_len + params->mem_conv + 1
                                                               : params->max_deviation;
-  h->nw_last = k.idwords[k.nrows - 1];
   // List size 1 needs no message identity at all (VCC:715-742 has no de-duplication): keep metrics
   // only, record one 4-bit decision per state and step, rebuild the message by traceback.
   h->survivor = h->L == 1 && !(params->flags & LVA_FLAG_EXACT_ONLY);
-  if (h->survivor) {
-    h->nw_last = 0;
-    for (uint32_t p = 0; p < k.nrows; p++) h->code.idwords[p] = 0;
-  }
+  h->all_one_bit = true;
+  for (uint32_t r = 1; r < k.nrows; r++) h->all_one_bit = h->all_one_bit && k.shift[r] == 1;
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -284,6 +315,30 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   for (auto &ev : h->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail("cudaEventCreate", e);
 
+  // ---- state geometry ----
+  h->window = (uint32_t)std::min<uint64_t>(k.nrows, 2ull * h->max_dev + 1ull);
+  h->piece_words = 192u * h->LP;
+  h->row_words = (k.nconv / 8u) * h->piece_words;
+  h->parity_words = (unsigned long long)h->window * h->row_words;
+  h->slot_words = (unsigned long long)k.nrows * k.nconv * 8ull;  // survivor layout: every row, one word per state
+  // nid ring: as many planes as boundary rows can be alive at once (rows [a-1, b) of a step), plus one
+  h->nid_ring = 1;
+  for (uint32_t p = 0; p < k.nrows; p++) {
+    uint32_t n = 0;
+    for (uint32_t q = p; q < k.nrows && q < p + h->window; q++) n += k.boundary[q];
+    h->nid_ring = std::max(h->nid_ring, n + 1);
+  }
+  h->nid_parity_words = (unsigned long long)h->nid_ring * k.nconv * 8ull * h->LP;
+  {
+    // interning table: distinct (chain id, chunk) pairs per read.  Sized generously; a probe chain
+    // that runs away raises a flag and the call is repeated with a larger table.
+    uint64_t want = (uint64_t)k.nconv * 4096ull;
+    if (const char *e2 = getenv("LVA_TAB_LOG2")) want = 1ull << std::min(28, std::max(10, atoi(e2)));
+    want = std::min<uint64_t>(std::max<uint64_t>(want, 1ull << 16), 1ull << 26);
+    h->tab_slots = next_pow2((uint32_t)want);
+    if (k.nchunks == 0) h->tab_slots = 1024;  // short messages: nothing is ever interned
+  }
+
   // ---- device code tables (constant memory slot) ----
   {
     std::lock_guard<std::mutex> g(g_slot_mutex);
@@ -293,57 +348,66 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   if (h->code_slot < 0) { lva_destroy(h); return fail(LVA_ERR_BAD_ARG, "too many live handles on this device"); }
   CodeDev &d = h->dev_code;
   d.mem = k.mem; d.nconv = k.nconv; d.G0 = k.G[0]; d.G1 = k.G[1]; d.init = k.init; d.fin = k.fin;
-  d.rc = k.rc ? 1 : 0; d.nrows = k.nrows; d.L = h->L; d.LP = h->LP; d.msg_len = k.msg_len; d.pad = 0;
-  unsigned long long off = 0;
-  for (uint32_t p = 0; p < k.nrows; p++) {
-    RowDev &r = d.row[p];
-    r.off = off;
-    r.vmask = k.vmask[p]; r.vval = k.vval[p];
-    const uint32_t idw = h->survivor ? 0u : k.idwords[p];
-    r.tile_words = 8u * (1u + idw) * h->LP * 32u;
-    r.block = k.block[p]; r.shift = k.shift[p]; r.idwords = (uint8_t)idw; r.dropmask = k.dropmask[p];
-    r.inv_lin = 0; r.lin1 = 0; r.pad0 = r.pad1 = 0; r.pad2 = 0;
-    if (p > 0) {  // linear map low predecessor bits -> emitted base (verified bijective by butterfly_structure_ok)
-      const uint32_t b0 = host_emitted_base(k, k.block[p], 0, 0, 0);
-      for (uint32_t xy = 0; xy < (1u << k.shift[p]); xy++) {
-        const uint32_t t = host_emitted_base(k, k.block[p], xy, 0, 0) ^ b0;
-        r.inv_lin |= (uint8_t)(xy << (2 * t));
-        if (xy == 1) r.lin1 = (uint8_t)t;
+  d.rc = k.rc ? 1 : 0; d.nrows = k.nrows; d.L = h->L; d.LP = h->LP; d.msg_len = k.msg_len;
+  d.window = h->window; d.nchunks = k.nchunks; d.last_plen = k.plen[k.nrows - 1]; d.nid_ring = h->nid_ring; d.pad = 0;
+  for (int i = 0; i < 16; i++) d.chunk_len[i] = k.chunk_len[i];
+  {
+    uint32_t nb = 0;  // boundary rows seen so far
+    uint8_t slot_of[kMaxRows] = {0};
+    for (uint32_t p = 0; p < k.nrows; p++) {
+      RowDev &r = d.row[p];
+      memset(&r, 0, sizeof(r));
+      r.vmask = k.vmask[p]; r.vval = k.vval[p];
+      r.block = k.block[p]; r.shift = k.shift[p];
+      r.app = k.app[p];
+      r.boundary = k.boundary[p];
+      if (r.boundary) { slot_of[p] = (uint8_t)(nb % h->nid_ring); nb++; }
+      r.nid_slot = slot_of[p];
+      r.post_boundary = p > 0 ? k.boundary[p - 1] : 0;
+      r.src_nid_slot = p > 0 ? slot_of[p - 1] : 0;
+      r.app_pos = (p > 0 && !r.post_boundary) ? k.plen[p - 1] : 0;
+      r.nohist = (k.plen[p] == 0 && k.chunk_of[p] == 0) ? 1 : 0;
+      if (p > 0) {  // linear map low predecessor bits -> emitted base (verified bijective by butterfly_structure_ok)
+        const uint32_t b0 = host_emitted_base(k, k.block[p], 0, 0, 0);
+        for (uint32_t xy = 0; xy < (1u << k.shift[p]); xy++) {
+          const uint32_t t = host_emitted_base(k, k.block[p], xy, 0, 0) ^ b0;
+          r.inv_lin |= (uint8_t)(xy << (2 * t));
+          if (xy == 1) r.lin1 = (uint8_t)t;
+        }
       }
     }
-    off += (unsigned long long)(k.nconv / kTileGroups) * r.tile_words;
   }
-  h->slot_words = off;
   if ((e = cudaMemcpyToSymbol(c_code, &d, sizeof(CodeDev), sizeof(CodeDev) * h->code_slot)) != cudaSuccess)
     return cuda_fail("cudaMemcpyToSymbol", e);
 
   // ---- kernel selection ----
   h->gen_tg = 0;
-  for (int tg : {32, 16, 8, 4}) {
+  for (int tg : {32, 16, 8}) {
     bool have = false;
 #define X(lp, tgc) if (h->LP == lp && tg == tgc) have = true;
     LVA_GENERIC_CASES(X)
 #undef X
     if (!have) continue;
-    size_t sm = generic_smem_bytes(h->LP, tg, h->nw_last);
+    size_t sm = generic_smem_bytes(h->LP, tg);
     if (sm <= (size_t)prop.sharedMemPerBlockOptin) { h->gen_tg = tg; h->gen_smem = sm; break; }
   }
-  if (!h->gen_tg) { lva_destroy(h); return fail(LVA_ERR_LIST_SIZE, "list_size x msg_len too large for shared memory"); }
+  if (!h->gen_tg) { lva_destroy(h); return fail(LVA_ERR_LIST_SIZE, "list_size too large for shared memory"); }
   if ((e = generic_prepare(h)) != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(generic)", e);
-  h->use_fast = !(params->flags & LVA_FLAG_EXACT_ONLY) && fast_supported(h->LP, h->nw_last);
-  if (h->use_fast && (e = fast_prepare(h->LP, h->nw_last)) != cudaSuccess)
+  h->use_fast = !(params->flags & LVA_FLAG_EXACT_ONLY) && (h->survivor || fast_supported(h->LP));
+  if (h->use_fast && !h->survivor && (e = fast_prepare(h->LP)) != cudaSuccess)
     return cuda_fail("cudaFuncSetAttribute(fast)", e);
 
   // ---- state memory: n_slots reads in flight, two parity buffers each ----
   size_t free_b = 0, total_b = 0;
   if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return cuda_fail("cudaMemGetInfo", e);
-  const size_t per_slot = (size_t)h->slot_words * 2 * 4;
+  size_t per_slot = h->survivor ? (size_t)h->slot_words * 2 * 4
+                                : (size_t)(h->parity_words + h->nid_parity_words) * 2 * 4 + (size_t)h->tab_slots * 8;
   size_t budget = (size_t)(free_b * 0.70);
   // default: enough reads in flight that one step launch is >= ~64 waves of CTAs (small codes are launch-bound otherwise), at least 64
   uint32_t slots = params->max_slots;
   if (!slots) {
     const uint64_t band_rows = std::min<uint64_t>(2ull * h->max_dev, k.nrows);
-    const uint64_t ctas_per_read = std::max<uint64_t>(1, band_rows * 2 * (k.nconv / 32));
+    const uint64_t ctas_per_read = std::max<uint64_t>(1, band_rows * (k.nconv / 32));
     slots = (uint32_t)std::min<uint64_t>(kMaxSlots, std::max<uint64_t>(64, (64ull * 4 * h->sm_count + ctas_per_read - 1) / ctas_per_read));
   }
   size_t per_slot_all = per_slot;
@@ -359,14 +423,23 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   if ((size_t)slots * per_slot > budget) slots = (uint32_t)(budget / per_slot);
   if (slots == 0) { lva_destroy(h); return fail(LVA_ERR_OOM, "not enough device memory for one read"); }
   h->n_slots = slots;
-  if (!h->d_state.ensure((size_t)slots * per_slot)) { lva_destroy(h); return fail(LVA_ERR_OOM, "state allocation failed"); }
-  if (!h->d_reads.ensure(sizeof(ReadDev) * slots) || !h->d_counters.ensure(64) ||
-      !h->d_final.ensure((size_t)slots * 8 * h->LP * (2 + h->nw_last) * 4)) {
+  const size_t state_bytes = h->survivor ? (size_t)slots * h->slot_words * 2 * 4 : (size_t)slots * h->parity_words * 2 * 4;
+  if (!h->d_state.ensure(state_bytes)) { lva_destroy(h); return fail(LVA_ERR_OOM, "state allocation failed"); }
+  if (!h->survivor && (!h->d_nid.ensure((size_t)slots * h->nid_parity_words * 2 * 4) ||
+                       !h->d_tab.ensure((size_t)slots * h->tab_slots * 8))) {
+    lva_destroy(h);
+    return fail(LVA_ERR_OOM, "chain table allocation failed");
+  }
+  if (!h->d_reads.ensure(sizeof(ReadDev) * slots) || !h->d_counters.ensure(kCounterBytes) ||
+      !h->d_final.ensure((size_t)slots * 8 * h->LP * kFinalWords * 4)) {
     lva_destroy(h);
     return fail(LVA_ERR_OOM, "allocation failed");
   }
-  cudaMemset(h->d_counters.p, 0, 64);
-  h->own_tma = h->use_fast && h->LP > 1 && getenv("LVA_NO_OWN_TMA") == nullptr && make_own_maps(h);
+  cudaMemset(h->d_counters.p, 0, kCounterBytes);
+  if (h->use_fast && !h->survivor) {
+    const std::string m = make_maps(h);
+    if (!m.empty()) { lva_destroy(h); return fail(LVA_ERR_CUDA, m); }
+  }
   if (status) *status = LVA_OK;
   return h;
 }
@@ -398,8 +471,14 @@ int lva_count_work(const lva_handle *h, uint32_t T, lva_work *out) {
       const double nst = std::ldexp(8.0, (int)k.mem - __builtin_popcount(k.vmask[p]));
       out->state_updates += nst;
       out->edge_acs += nst * (p == 0 ? 1.0 : (k.block[p] == 0 ? 3.0 : 5.0));
-      // one read of the previous list + one write of the new list, LP slots of (1+nw) words
-      out->state_bytes += nst * 2.0 * 4.0 * h->LP * (1 + k.idwords[p]) + (h->survivor ? nst * 0.5 : 0.0);
+      if (h->survivor) {
+        out->state_bytes += nst * 8.5;  // metric read + metric written + 4-bit decision
+      } else {
+        // states some conv transition reaches (one-bit rows: two of the four bases): one read and one
+        // write of the list, LP slots of 3 words, plus the published chain id on boundary rows
+        const double live = p == 0 ? 8.0 : (k.shift[p] == 1 ? nst * 0.5 : nst);
+        out->state_bytes += live * 4.0 * h->LP * (6.0 + (k.boundary[p] ? 1.0 : 0.0));
+      }
     }
   }
   return LVA_OK;
@@ -456,16 +535,20 @@ int lva_encode(uint32_t mem_conv, uint32_t rate, const uint8_t *msg, uint32_t ms
   return LVA_OK;
 }
 
-static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs, uint32_t n_reads,
-                       uint8_t *out_bits, float *out_scores, uint32_t *out_counts, int32_t *out_status) {
+}  // extern "C"
+
+// read i owns posterior blocks [starts[i], ends[i]) of d_post
+static int decode_core(lva_handle *h, const float *d_post, const uint64_t *starts, const uint64_t *ends, uint32_t n_reads,
+                       const CrcReq &crc, uint8_t *out_bits, float *out_scores, uint32_t *out_counts,
+                       int32_t *out_status) {
   const CodeSpec &k = h->code;
-  const uint32_t L = h->L, LP = h->LP, msg_len = k.msg_len, planes = 2 + h->nw_last;  // metric, history, CRC word
+  const uint32_t L = h->L, LP = h->LP, msg_len = k.msg_len;
   const float NEG = -std::numeric_limits<float>::infinity();
 
   std::vector<uint32_t> order;
   order.reserve(n_reads);
   for (uint32_t i = 0; i < n_reads; i++) {
-    const uint64_t T = offs[i + 1] - offs[i];
+    const uint64_t T = ends[i] >= starts[i] ? ends[i] - starts[i] : 0;
     out_counts[i] = 0;
     if (T < (uint64_t)k.nrows + 1 || T > 0xFFFFFFFFull) {  // VCC:600-601
       if (out_status) out_status[i] = LVA_ERR_POST_TOO_SMALL;
@@ -474,9 +557,8 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     if (out_status) out_status[i] = LVA_OK;
     order.push_back(i);
   }
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-    return offs[x + 1] - offs[x] > offs[y + 1] - offs[y];
-  });
+  auto len_of = [&](uint32_t i) { return ends[i] - starts[i]; };
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return len_of(x) > len_of(y); });
 
   const uint32_t dev2 = 2u * h->max_dev;
   float acc_kernel = 0.f, acc_d2h = 0.f;
@@ -484,7 +566,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
   const uint32_t dec_rows = (uint32_t)std::min<uint64_t>((uint64_t)dev2 > 0 ? dev2 : 1, k.nrows);
   size_t chunk_cap = h->n_slots;
   if (h->survivor && !order.empty()) {  // decisions: T x band rows x conv states words per read in flight
-    const uint64_t Tlongest = offs[order[0] + 1] - offs[order[0]];
+    const uint64_t Tlongest = len_of(order[0]);
     const uint64_t per_read = Tlongest * dec_rows * k.nconv * 4ull;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -495,7 +577,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     const uint32_t ns = (uint32_t)std::min<size_t>(chunk_cap, order.size() - c0);
     // ---- per-slot control + band tables ----
     size_t band_total = 0;
-    for (uint32_t s = 0; s < ns; s++) band_total += offs[order[c0 + s] + 1] - offs[order[c0 + s]];
+    for (uint32_t s = 0; s < ns; s++) band_total += len_of(order[c0 + s]);
     const size_t stage_bytes = sizeof(ReadDev) * ns + band_total * sizeof(uint16_t);
     if (!h->h_stage.ensure(stage_bytes) || !h->d_band.ensure(band_total * sizeof(uint16_t) + 16)) {
       h->err = "staging allocation failed";
@@ -507,9 +589,9 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     size_t bo = 0;
     for (uint32_t s = 0; s < ns; s++) {
       const uint32_t i = order[c0 + s];
-      const uint32_t T = (uint32_t)(offs[i + 1] - offs[i]);
+      const uint32_t T = (uint32_t)len_of(i);
       Ts[s] = T;
-      rd[s].post_block = offs[i];
+      rd[s].post_block = starts[i];
       rd[s].T = T;
       rd[s].band_off = (uint32_t)bo;
       for (uint32_t t = 0; t < T; t++) band[bo + t] = (uint16_t)band_start(t, T, k.nrows, h->max_dev);
@@ -529,11 +611,15 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
       }
     }
 
-    // ---- initialise the slots ----
-    const unsigned long long words = (unsigned long long)ns * 2 * h->slot_words;
-    lva_fill_neg_inf<<<h->sm_count * 8, 256, 0, h->stream>>>((uint32_t *)h->d_state.p, words);
-    lva_seed_start<<<(ns * 8 + 127) / 128, 128, 0, h->stream>>>((uint32_t *)h->d_state.p, h->slot_words,
-                                                                  h->code_slot, ns);
+    // ---- initialise the slots: every metric -inf, the start state seeded, chain tables empty ----
+    if (h->survivor) {
+      lva_fill_u32x4<<<h->sm_count * 8, 256, 0, h->stream>>>((uint32_t *)h->d_state.p, (unsigned long long)ns * 2 * h->slot_words, 0xff800000u);
+      lva_seed_start_l1<<<(ns * 8 + 127) / 128, 128, 0, h->stream>>>((uint32_t *)h->d_state.p, h->slot_words, h->code_slot, ns);
+    } else {
+      lva_fill_u32x4<<<h->sm_count * 8, 256, 0, h->stream>>>((uint32_t *)h->d_state.p, (unsigned long long)ns * 2 * h->parity_words, 0xff800000u);
+      lva_seed_start<<<(ns * 8 + 127) / 128, 128, 0, h->stream>>>((uint32_t *)h->d_state.p, h->parity_words, h->piece_words, h->code_slot, ns);
+      if (k.nchunks > 0) CK(cudaMemsetAsync(h->d_tab.p, 0xFF, (size_t)ns * h->tab_slots * 8, h->stream));
+    }
     h->timing.launches += 2;
     CK(cudaGetLastError());
 
@@ -541,72 +627,69 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
     CK(cudaEventRecord(h->ev[2], h->stream));
     StepArgs a{};
     a.state = (uint32_t *)h->d_state.p;
-    a.slot_words = h->slot_words;
+    a.nid = (uint32_t *)h->d_nid.p;
+    a.tab = (unsigned long long *)h->d_tab.p;
+    a.parity_words = h->parity_words;
+    a.nid_parity_words = h->nid_parity_words;
     a.post = d_post;
     a.counters = (unsigned long long *)h->d_counters.p;
+    a.row_words = h->row_words;
+    a.piece_words = h->piece_words;
+    a.tab_mask = h->tab_slots - 1;
     a.dev2 = dev2;
     a.code_slot = h->code_slot;
-    a.dec = h->survivor ? (uint32_t *)h->d_dec.p : nullptr;
-    a.dec_slot_words = dec_slot_words;
-    a.dec_rows = dec_rows;
-    a.own_tma = h->own_tma ? 1u : 0u;
-    // developer switch for A/B runs: list size 1 through the tile-staging kernel lva_step_fast<1,0>
-    static const bool no_l1_kernel = getenv("LVA_NO_L1_KERNEL") != nullptr;
+    a.row_lo = 0;
+    a.row_hi = k.nrows;
+    ClearArgs clr{};
+    clr.state = a.state;
+    clr.parity_words = h->parity_words;
+    clr.row_words = h->row_words;
+    clr.piece_words = h->piece_words;
+    clr.code_slot = h->code_slot;
     const uint32_t Tmax = Ts[0];
     uint32_t active = ns;
     for (uint32_t t = 0; t < Tmax; t++) {
       while (active > 0 && Ts[active - 1] <= t) active--;  // reads are sorted by T, longest first
-      // rows touched this step: union over active reads of [a, b)
-      uint32_t lo = 0xffffffffu, hi = 0;
+      a.t = t;
+      uint32_t span = 0;
+      bool any_clear = false;
       for (uint32_t s = 0; s < active; s++) {
         const uint32_t st = band[rd[s].band_off + t], en = band_end(st, k.nrows, h->max_dev);
-        lo = std::min(lo, st);
-        hi = std::max(hi, en);
-      }
-      if (hi <= lo) continue;
-      a.t = t;
-      for (uint32_t s = 0; s < active; s++) {
-        a.band_a[s] = band[rd[s].band_off + t];
+        span = std::max(span, en - st);
+        a.band_a[s] = (uint16_t)st;
         a.post_blk[s] = (uint32_t)(rd[s].post_block + t);
+        clr.row[s] = 0xFFFFu;
+        if (!h->survivor && t > 0 && en > 0) {
+          // a row entering the band re-uses a window slot: wipe it first (lva_clear_rows); the band
+          // end grows by at most one row per step (T >= nstate_pos + 1)
+          const uint32_t en_prev = band_end(band[rd[s].band_off + t - 1], k.nrows, h->max_dev);
+          if (en > en_prev && en - 1 >= h->window) { clr.row[s] = (uint16_t)(en - 1); any_clear = true; }
+        }
       }
-      if (h->use_fast && h->survivor && !no_l1_kernel) {
-        L1Args l1{a.state, a.slot_words, a.post, a.dec, a.dec_slot_words, (const ReadDev *)h->d_reads.p,
-                  (const uint16_t *)h->d_band.p, a.dec_rows, t, a.dev2, a.code_slot};
+      if (span == 0) continue;
+      if (any_clear) {
+        lva_clear_rows<<<dim3(std::max<uint32_t>(1, (k.nconv / 8) * (16 * LP) * 2 / 256), active), 256, 0, h->stream>>>(clr);
+        h->timing.launches++;
+      }
+      if (h->use_fast && h->survivor) {
+        L1Args l1{a.state, h->slot_words, a.post, (uint32_t *)h->d_dec.p, dec_slot_words, (const ReadDev *)h->d_reads.p,
+                  (const uint16_t *)h->d_band.p, dec_rows, t, a.dev2, a.code_slot};
         cudaError_t e = l1_launch_step(h->stream, l1, k, active);
         if (e != cudaSuccess) { h->err = std::string("L=1 step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
-        h->timing.step_launches++;
       } else if (h->use_fast) {
-        cudaError_t e = fast_launch_step(h->LP, h->stream, a, k, lo, hi, active, &h->timing.step_launches, h->own_maps);
+        cudaError_t e = fast_launch_step(h->LP, h->stream, a, k, span, active, h->maps, h->all_one_bit);
         if (e != cudaSuccess) { h->err = std::string("fast step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
       } else {
-        a.row_lo = 0;
-        a.row_hi = k.nrows;
-        uint32_t span = 0;
-        for (uint32_t s = 0; s < active; s++) {
-          const uint32_t st = band[rd[s].band_off + t];
-          span = std::max(span, band_end(st, k.nrows, h->max_dev) - st);
-        }
         dim3 grid(k.nconv / h->gen_tg, span, active);
         cudaError_t e = generic_launch(h, grid, a);
         if (e != cudaSuccess) { h->err = std::string("generic step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
-        h->timing.step_launches++;
       }
+      h->timing.step_launches++;
     }
     CK(cudaEventRecord(h->ev[3], h->stream));
 
     // ---- collect the candidate lists of the end state ----
-    FinalArgs f{};
-    f.state = (const uint32_t *)h->d_state.p;
-    f.slot_words = h->slot_words;
-    f.reads = (const ReadDev *)h->d_reads.p;
-    f.out = (uint32_t *)h->d_final.p;
-    f.code_slot = h->code_slot;
-    f.n_slots = ns;
-    f.crc_pad = h->crc_pad;
     const uint32_t nfin = ns * 8 * LP;
-    lva_collect_final<<<(nfin + 127) / 128, 128, 0, h->stream>>>(f);
-    h->timing.launches += 1;
-    CK(cudaGetLastError());
     if (h->survivor) {
       TraceArgs tr{};
       tr.state = (const uint32_t *)h->d_state.p;
@@ -619,20 +702,49 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
       tr.out = (uint32_t *)h->d_trace.p;
       tr.code_slot = h->code_slot;
       tr.n_slots = ns;
-      tr.crc_pad = h->crc_pad;
+      tr.crc_pad = crc.pad;
       lva_traceback<<<(ns + 63) / 64, 64, 0, h->stream>>>(tr);
       h->timing.launches += 1;
       CK(cudaGetLastError());
+      CK(cudaEventRecord(h->ev[4], h->stream));
       CK(cudaMemcpyAsync(h->h_trace.p, h->d_trace.p, (size_t)ns * 12 * 4, cudaMemcpyDeviceToHost, h->stream));
       h->timing.d2h_bytes += (size_t)ns * 12 * 4;
+    } else {
+      FinalArgs f{};
+      f.state = (const uint32_t *)h->d_state.p;
+      f.tab = (const unsigned long long *)h->d_tab.p;
+      f.parity_words = h->parity_words;
+      f.reads = (const ReadDev *)h->d_reads.p;
+      f.out = (uint32_t *)h->d_final.p;
+      f.row_words = h->row_words;
+      f.piece_words = h->piece_words;
+      f.tab_slots = h->tab_slots;
+      f.code_slot = h->code_slot;
+      f.n_slots = ns;
+      f.crc_pad = crc.pad;
+      lva_collect_final<<<(nfin + 127) / 128, 128, 0, h->stream>>>(f);
+      h->timing.launches += 1;
+      CK(cudaGetLastError());
+      const size_t fin_bytes = (size_t)nfin * kFinalWords * 4;
+      if (!h->h_final.ensure(fin_bytes)) { h->err = "pinned allocation failed"; return LVA_ERR_OOM; }
+      CK(cudaEventRecord(h->ev[4], h->stream));
+      CK(cudaMemcpyAsync(h->h_final.p, h->d_final.p, fin_bytes, cudaMemcpyDeviceToHost, h->stream));
+      h->timing.d2h_bytes += fin_bytes;
     }
-    const size_t fin_bytes = (size_t)nfin * planes * 4;
-    if (!h->h_final.ensure(fin_bytes)) { h->err = "pinned allocation failed"; return LVA_ERR_OOM; }
-    CK(cudaEventRecord(h->ev[4], h->stream));
-    CK(cudaMemcpyAsync(h->h_final.p, h->d_final.p, fin_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->survivor && k.nchunks > 0) {  // keys per chain table of this chunk of reads, then reset for the next
+      static_assert(sizeof(unsigned long long) == 8, "");
+      if (!h->h_post.ensure(ns * 8)) { h->err = "pinned allocation failed"; return LVA_ERR_OOM; }
+      CK(cudaMemcpyAsync(h->h_post.p, (unsigned long long *)h->d_counters.p + 8, ns * 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemsetAsync((unsigned long long *)h->d_counters.p + 8, 0, ns * 8, h->stream));
+    }
     CK(cudaEventRecord(h->ev[5], h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->timing.d2h_bytes += fin_bytes;
+    if (!h->survivor && k.nchunks > 0)
+      for (uint32_t s = 0; s < ns; s++) {
+        const unsigned long long n = reinterpret_cast<const unsigned long long *>(h->h_post.p)[s];
+        h->timing.chain_inserts += n;
+        h->timing.chain_keys_max = std::max<uint64_t>(h->timing.chain_keys_max, n);
+      }
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
     acc_kernel += ms;
@@ -657,14 +769,14 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
       } else
       for (uint32_t crf = 0; crf < 8; crf++)
         for (uint32_t j = 0; j < L; j++) {
-          const uint32_t *e = fw + ((size_t)(s * 8 + crf) * LP + j) * planes;
+          const uint32_t *e = fw + ((size_t)(s * 8 + crf) * LP + j) * kFinalWords;
           float sc;
           memcpy(&sc, e, 4);
           if (sc != NEG) {
             FinalEntry fe;
             fe.score = sc;
-            for (uint32_t w = 0; w < h->nw_last; w++) fe.id[w] = e[1 + w];
-            fe.crcw = e[1 + h->nw_last];
+            for (uint32_t w = 0; w < 8; w++) fe.id[w] = e[1 + w];
+            fe.crcw = e[9];
             fin.push_back(fe);
           }
         }
@@ -672,16 +784,16 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
                 [](const FinalEntry &p1, const FinalEntry &p2) -> bool { return p1.score > p2.score; });
       if (fin.size() > L) fin.resize(L);
       out_counts[i] = (uint32_t)fin.size();
-      if (h->crc_pad >= 0) {  // helper.decode_list_CRC_index: first entry whose CRC matches and index < num_oligos
+      if (crc.pad >= 0) {  // helper.decode_list_CRC_index: first entry whose CRC matches and index < num_oligos
         int32_t choice = -1;
         for (size_t e = 0; e < fin.size(); e++) {
           const bool ok = (fin[e].crcw & kCrcOk) != 0;
           const uint32_t idx = fin[e].crcw & 0xfffu;
-          if (h->crc_ok_out) h->crc_ok_out[(size_t)i * L + e] = ok ? 1 : 0;
-          if (h->crc_index_out) h->crc_index_out[(size_t)i * L + e] = (uint16_t)idx;
-          if (choice < 0 && ok && idx < h->crc_num_oligos) choice = (int32_t)e;
+          if (crc.ok_out) crc.ok_out[(size_t)i * L + e] = ok ? 1 : 0;
+          if (crc.index_out) crc.index_out[(size_t)i * L + e] = (uint16_t)idx;
+          if (choice < 0 && ok && idx < crc.num_oligos) choice = (int32_t)e;
         }
-        if (h->crc_choice_out) h->crc_choice_out[i] = choice;
+        if (crc.choice_out) crc.choice_out[i] = choice;
       }
       for (size_t e = 0; e < fin.size(); e++) {
         if (out_scores) out_scores[(size_t)i * L + e] = fin[e].score;
@@ -694,73 +806,104 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *offs,
       }
     }
   }
-  h->timing.kernel_ms = acc_kernel;
-  h->timing.d2h_ms = acc_d2h;
-  h->timing.launches += h->timing.step_launches;
+  h->timing.kernel_ms += acc_kernel;
+  h->timing.d2h_ms += acc_d2h;
   return LVA_OK;
 }
 
-static int decode_entry(lva_handle *h, const float *post, bool post_on_device, const uint64_t *offs,
-                        uint32_t n_reads, uint8_t *out_bits, float *out_scores, uint32_t *out_counts,
-                        int32_t *out_status) {
+// `post` host or device memory; read i = blocks [starts[i], ends[i]).
+static int decode_entry(lva_handle *h, const float *post, bool post_on_device, const uint64_t *starts,
+                        const uint64_t *ends, uint32_t n_reads, const CrcReq &crc, uint8_t *out_bits, float *out_scores,
+                        uint32_t *out_counts, int32_t *out_status) {
   if (!h) return LVA_ERR_BAD_ARG;
   if (n_reads == 0) return LVA_OK;
-  if (!post || !offs || !out_bits || !out_counts) { h->err = "null argument"; return LVA_ERR_BAD_ARG; }
-  if (offs[n_reads] > 0xFFFF0000ull) { h->err = "batch too large (block index must fit 32 bits)"; return LVA_ERR_BAD_ARG; }
+  if (!post || !starts || !ends || !out_bits || !out_counts) { h->err = "null argument"; return LVA_ERR_BAD_ARG; }
+  uint64_t lo = ~0ull, hi = 0;
+  for (uint32_t i = 0; i < n_reads; i++) {
+    if (ends[i] < starts[i]) { h->err = "block range ends before it starts"; return LVA_ERR_BAD_ARG; }
+    lo = std::min(lo, starts[i]);
+    hi = std::max(hi, ends[i]);
+  }
+  if (hi > 0xFFFF0000ull) { h->err = "batch too large (block index must fit 32 bits)"; return LVA_ERR_BAD_ARG; }
   CK(cudaSetDevice(h->device));
   h->timing = lva_timing{};
-  CK(cudaMemsetAsync(h->d_counters.p, 0, 64, h->stream));
   CK(cudaEventRecord(h->ev[0], h->stream));
   const float *d_post = post;
   if (!post_on_device) {
-    const uint64_t b0 = offs[0], b1 = offs[n_reads];
-    const size_t bytes = (size_t)(b1 - b0) * 160;
+    const size_t bytes = (size_t)(hi - lo) * 160;
     if (!h->d_post.ensure(bytes + 16)) { h->err = "posterior device allocation failed"; return LVA_ERR_OOM; }
-    // Staged so that read i's block b sits at d_post + (block_offsets[i] + b) * 40, as with device input
-    CK(cudaMemcpyAsync(h->d_post.p, post + b0 * 40, bytes, cudaMemcpyHostToDevice, h->stream));
-    d_post = reinterpret_cast<const float *>(h->d_post.p) - b0 * 40;
+    // Staged so that block b of the caller's array sits at d_post + b * 40, as with device input
+    CK(cudaMemcpyAsync(h->d_post.p, post + lo * 40, bytes, cudaMemcpyHostToDevice, h->stream));
+    d_post = reinterpret_cast<const float *>(h->d_post.p) - lo * 40;
     h->timing.h2d_bytes += bytes;
   }
   CK(cudaEventRecord(h->ev[1], h->stream));
-  int st = decode_core(h, d_post, offs, n_reads, out_bits, out_scores, out_counts, out_status);
-  if (st != LVA_OK) return st;
+  for (int attempt = 0;; attempt++) {
+    CK(cudaMemsetAsync(h->d_counters.p, 0, kCounterBytes, h->stream));
+    h->timing.chain_keys_max = 0;
+    int st = decode_core(h, d_post, starts, ends, n_reads, crc, out_bits, out_scores, out_counts, out_status);
+    if (st != LVA_OK) return st;
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaMemcpy(cnt, h->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost));
+    h->timing.exact_fallbacks = cnt[0];
+    h->timing.chain_table_slots = h->tab_slots;
+    if (cnt[1] == 0) break;
+    // a chain table filled up: every result of this call is suspect.  Grow the tables and decode again.
+    if (attempt == 3 || h->tab_slots >= (1u << 27)) { h->err = "chain table overflow"; return LVA_ERR_OOM; }
+    h->tab_slots *= 4;
+    h->timing.table_regrows++;
+    if (!h->d_tab.ensure((size_t)h->n_slots * h->tab_slots * 8)) { h->err = "chain table growth failed"; return LVA_ERR_OOM; }
+  }
   CK(cudaEventRecord(h->ev[6], h->stream));
   CK(cudaEventSynchronize(h->ev[6]));
   cudaEventElapsedTime(&h->timing.total_ms, h->ev[0], h->ev[6]);
   cudaEventElapsedTime(&h->timing.h2d_ms, h->ev[0], h->ev[1]);
-  unsigned long long fb = 0;
-  CK(cudaMemcpy(&fb, h->d_counters.p, sizeof(fb), cudaMemcpyDeviceToHost));
-  h->timing.exact_fallbacks = fb;
+  h->timing.launches += h->timing.step_launches;
   return LVA_OK;
 }
 
+namespace {
+struct OffsetRanges {  // cumulative offsets -> (starts, ends)
+  const uint64_t *starts, *ends;
+  explicit OffsetRanges(const uint64_t *offs) : starts(offs), ends(offs ? offs + 1 : nullptr) {}
+};
+}  // namespace
+
+extern "C" {
+
 int lva_decode_batch(lva_handle *h, const float *post, const uint64_t *block_offsets, uint32_t n_reads,
                      uint8_t *out_bits, float *out_scores, uint32_t *out_counts, int32_t *out_status) {
-  return decode_entry(h, post, false, block_offsets, n_reads, out_bits, out_scores, out_counts, out_status);
+  OffsetRanges r(block_offsets);
+  return decode_entry(h, post, false, r.starts, r.ends, n_reads, CrcReq{}, out_bits, out_scores, out_counts, out_status);
 }
+
 int lva_decode_batch_crc(lva_handle *h, const float *post, const uint64_t *block_offsets, uint32_t n_reads,
                          int32_t pad, uint32_t num_oligos, uint8_t *out_bits, float *out_scores,
                          uint32_t *out_counts, int32_t *out_status, uint8_t *out_crc_ok, uint16_t *out_index,
                          int32_t *out_choice) {
-  if (!h) return LVA_ERR_BAD_ARG;
-  h->crc_pad = pad ? 1 : 0;
-  h->crc_num_oligos = num_oligos;
-  h->crc_ok_out = out_crc_ok;
-  h->crc_index_out = out_index;
-  h->crc_choice_out = out_choice;
+  CrcReq crc;
+  crc.pad = pad ? 1 : 0;
+  crc.num_oligos = num_oligos;
+  crc.ok_out = out_crc_ok;
+  crc.index_out = out_index;
+  crc.choice_out = out_choice;
   if (out_choice) for (uint32_t i = 0; i < n_reads; i++) out_choice[i] = -1;
-  const int st = decode_entry(h, post, false, block_offsets, n_reads, out_bits, out_scores, out_counts, out_status);
-  h->crc_pad = -1;
-  h->crc_ok_out = nullptr;
-  h->crc_index_out = nullptr;
-  h->crc_choice_out = nullptr;
-  return st;
+  OffsetRanges r(block_offsets);
+  return decode_entry(h, post, false, r.starts, r.ends, n_reads, crc, out_bits, out_scores, out_counts, out_status);
 }
 
 int lva_decode_batch_device(lva_handle *h, const float *post_dev, const uint64_t *block_offsets,
                             uint32_t n_reads, uint8_t *out_bits, float *out_scores, uint32_t *out_counts,
                             int32_t *out_status) {
-  return decode_entry(h, post_dev, true, block_offsets, n_reads, out_bits, out_scores, out_counts, out_status);
+  OffsetRanges r(block_offsets);
+  return decode_entry(h, post_dev, true, r.starts, r.ends, n_reads, CrcReq{}, out_bits, out_scores, out_counts, out_status);
+}
+
+int lva_decode_ranges(lva_handle *h, const float *post, int32_t post_on_device, const uint64_t *block_starts,
+                      const uint64_t *block_ends, uint32_t n_reads, uint8_t *out_bits, float *out_scores,
+                      uint32_t *out_counts, int32_t *out_status) {
+  return decode_entry(h, post, post_on_device != 0, block_starts, block_ends, n_reads, CrcReq{}, out_bits, out_scores,
+                      out_counts, out_status);
 }
 
 }  // extern "C"

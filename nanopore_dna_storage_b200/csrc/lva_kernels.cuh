@@ -1,10 +1,11 @@
-// Trellis kernels of the B200 list-Viterbi decoder (sm_100a).
+// Trellis kernels of the B200 list-Viterbi decoder (sm_100a): shared pieces.
 //
 // One launch = one time step t of the reference's outer loop
 // (/root/reference/viterbi/viterbi_convolutional_code.cpp:667-805, "VCC") for a batch of reads:
 // grid = (conv tiles, band rows, read slots).  A CTA owns the 32 predecessor conv states of one
-// tile of row p-1 (staged once, reused by every target they feed) and computes the TG*8 product
+// tile of row p-1 (staged once, reused by every target they feed) and computes the product
 // states of row p that those predecessors reach -- the butterfly of Appendix B in SURVEY.md.
+// Data model (3-word list entries, chain ids, octet pieces, row window): lva_device.cuh.
 #pragma once
 #include <cstdint>
 #include <cuda.h>
@@ -51,13 +52,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
       "r"(phase)
       : "memory");
 }
-// 3-D tiled copy global -> shared through the TMA unit (SASS: UTMALDG), completion on an mbarrier.
+// Tiled copies global -> shared through the TMA unit (SASS: UTMALDG), completion on an mbarrier.
 // `map` must live in kernel-parameter space (const __grid_constant__ CUtensorMap).
 __device__ __forceinline__ void tensor3d_g2s(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
           smem_u32(dst)),
       "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tensor5d_g2s(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
       : "memory");
 }
 // 1-D bulk copy global -> shared through the TMA unit (SASS: UBLKCP), completion on an mbarrier
@@ -93,50 +102,84 @@ __device__ __forceinline__ uint32_t emitted_base(const CodeDev &K, uint32_t blk,
   return r ? 2u * o3 + o1 : 2u * o1 + o3;
 }
 
+// The history bits a move appends, in absolute order (oldest at bit 0): the newest `app` of the
+// `shift` bits xy that fall off the low end of the predecessor register (its bit 0 is the oldest).
+__device__ __forceinline__ uint32_t appended_bits(uint32_t xy, uint32_t shift, uint32_t app) {
+  return app == 0 ? 0u : (app == shift ? xy : (xy >> 1));
+}
+
+// Where things live in the state buffer (lva_device.cuh)
+__device__ __forceinline__ unsigned long long row_base(const StepArgs &A, const CodeDev &K, uint32_t z, uint32_t parity,
+                                                       uint32_t p) {
+  return ((unsigned long long)z * 2 + parity) * A.parity_words + (unsigned long long)(p % K.window) * A.row_words;
+}
+__device__ __forceinline__ unsigned long long nid_base(const StepArgs &A, const CodeDev &K, uint32_t z, uint32_t parity,
+                                                       uint32_t ring_slot) {
+  return ((unsigned long long)z * 2 + parity) * A.nid_parity_words +
+         (unsigned long long)ring_slot * ((unsigned long long)K.nconv * 8u * K.LP);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain ids: insert-or-get of the key (parent id, chunk bits) in the read's open-addressing table;
+// the id is the slot index.  Slots go from empty to a key exactly once and never change again, so
+// a cached load that still shows "empty" only costs the compare-and-swap that follows, and a
+// non-empty value is always the truth.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t key_hash(unsigned long long key) {
+  return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32);
+}
+__device__ __noinline__ uint32_t intern_chunk(unsigned long long *tab, uint32_t mask, uint32_t id, uint32_t chunk,
+                                              unsigned long long *counters, uint32_t z) {
+  const unsigned long long key = ((unsigned long long)id << 32) | chunk;
+  uint32_t h = key_hash(key) & mask;
+  for (uint32_t n = 0; n < 512u; n++) {
+    unsigned long long cur = tab[h];
+    if (cur == kEmptyKey) {
+      cur = atomicCAS(tab + h, kEmptyKey, key);
+      if (cur == kEmptyKey) {
+        atomicAdd(counters + 8 + z, 1ull);  // keys of this read's table
+        return h;
+      }
+    }
+    if (cur == key) return h;
+    h = (h + 1u) & mask;
+  }
+  atomicExch(counters + 1, 1ull);  // far too long a probe chain: the host repeats the call with larger tables
+  return h;
+}
+
 // Thread geometry of one CTA: which target state it owns and where its predecessors sit.
 struct Target {
   uint32_t c;        // target conv state
   int s;             // target crf state 0..7 (0-3 flip, 4-7 flop)
   int src_g;         // local index (0..TG-1) of the predecessor conv state inside the staged tile, -1 none
-  uint32_t drop;     // message bits leaving the register on this move (already masked)
-  bool valid;        // (c & vmask) == vval
+  uint32_t xy;       // the bits that fall off the predecessor register on this move
+  bool valid;        // (c & vmask) == vval and some conv transition emits base s
 };
 
-// q = index among the TG*4 (target group, base) pairs of the tile; role 0 = flip, 1 = flop
+// q = index among the TG*4 (target group, base) pairs of the tile; role 0 = flip, 1 = flop   (p > 0)
 template <int TG>
-__device__ __forceinline__ Target locate_target_q(const CodeDev &K, const RowDev &R, uint32_t p, uint32_t tile,
-                                                  int q, int role) {
+__device__ __forceinline__ Target locate_target_q(const CodeDev &K, const RowDev &R, uint32_t tile, int q, int role) {
   Target T;
   const int tg = q >> 2, b = q & 3;
   T.s = b + 4 * role;
-  const int sh = p == 0 ? 1 : R.shift;
+  const int sh = R.shift;
   const int per = TG >> sh;                 // consecutive targets per run
   const uint32_t run = tg / per, idx = tg % per;
   const uint32_t lo = tile * per + idx;
   T.c = (run << (K.mem - sh)) | lo;
-  T.valid = (T.c & R.vmask) == R.vval;
   T.src_g = -1;
-  T.drop = 0;
-  if (p > 0) {
-    const uint32_t c_shift = lo << sh;      // == (c << sh) & (nconv-1)
-    const uint32_t in1 = sh == 1 ? run : (run & 1u), in2 = run >> 1;
-    for (uint32_t xy = 0; xy < (1u << sh); xy++) {
-      if (emitted_base(K, R.block, c_shift | xy, in1, in2) == (uint32_t)b) {
-        T.src_g = (int)((idx << sh) | xy);
-        // bits falling off the low end of the predecessor register, oldest first
-        const uint32_t fell = sh == 1 ? xy : (((xy & 1u) << 1) | (xy >> 1));
-        T.drop = fell & R.dropmask;
-      }
+  T.xy = 0;
+  const uint32_t c_shift = lo << sh;      // == (c << sh) & (nconv-1)
+  const uint32_t in1 = sh == 1 ? run : (run & 1u), in2 = run >> 1;
+  for (uint32_t xy = 0; xy < (1u << sh); xy++) {
+    if (emitted_base(K, R.block, c_shift | xy, in1, in2) == (uint32_t)b) {
+      T.src_g = (int)((idx << sh) | xy);
+      T.xy = xy;
     }
   }
+  T.valid = (T.c & R.vmask) == R.vval && T.src_g >= 0;
   return T;
-}
-
-template <int TG>
-__device__ __forceinline__ Target locate_target(const CodeDev &K, const RowDev &R, uint32_t p, uint32_t tile,
-                                                int tid) {
-  const int role = tid >= TG * 4;
-  return locate_target_q<TG>(K, R, p, tile, tid - role * TG * 4, role);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -144,56 +187,48 @@ __device__ __forceinline__ Target locate_target(const CodeDev &K, const RowDev &
 // (VCC:743-800) and its L=1 scan (VCC:715-742), ties included.  Used for every state in
 // validation mode and as the fallback of the register fast path whenever two list heads tie.
 //
-//   src   : staged predecessor tile   [crf][plane][slot][TG]      (shared memory)
+//   src   : staged predecessor tile   [plane][crf][slot][TG]      (shared memory)
 //   mine  : this thread's own list    [plane][slot] stride NT     (shared memory; holds the STAY
 //           list of row p on entry, receives the new list on exit)
 //   post  : the 40 transition scores of step t
+// Returns the number of entries of the new list.
 // ---------------------------------------------------------------------------------------------
-// View of the lists one target state merges: its own (stay) list, copied to local memory, and
-// the predecessor lists inside the staged tile.
 template <int LP>
 struct MergeLists {
   const uint32_t *src;   // staged tile base + src_g
-  int list_stride, plane_stride, tg;  // in words
-  int nws, nwd, sh, s;
-  uint32_t drop;
+  int tg;                // words between slots of a staged list
+  int s;
+  uint32_t keep, app;    // identity of a move candidate: (id, (partial & keep) | app)
   float st_sc[LP];
-  uint32_t st_id[LP * kMaxIdWords];
+  uint32_t st_id[LP], st_pt[LP];
 
-  __device__ __forceinline__ float src_score(int k, int j) const {
-    return __uint_as_float(src[k * list_stride + j * tg]);
-  }
+  __device__ __forceinline__ float src_score(int k, int j) const { return __uint_as_float(src[(k * LP + j) * tg]); }
   __device__ __forceinline__ float score(int k, int j) const { return k == s ? st_sc[j] : src_score(k, j); }
-  // message history (nwd words) the candidate "entry j of list k" would carry at the target
-  __device__ __forceinline__ void history(int k, int j, uint32_t *id) const {
+  __device__ __forceinline__ void identity(int k, int j, uint32_t &id, uint32_t &pt) const {
     if (k == s) {
-      for (int w = 0; w < nwd; w++) id[w] = st_id[j * kMaxIdWords + w];
+      id = st_id[j];
+      pt = st_pt[j];
     } else {
-      uint32_t prev = 0;
-      for (int w = 0; w < nwd; w++) {
-        uint32_t old = 0;
-        if (w < nws) old = src[k * list_stride + (1 + w) * plane_stride + j * tg];
-        id[w] = (old << sh) | (w == 0 ? drop : (prev >> (32 - sh)));
-        prev = old;
-      }
+      id = src[((8 + k) * LP + j) * tg];
+      pt = (src[((16 + k) * LP + j) * tg] & keep) | app;
     }
   }
 };
 
 template <int LP>
-__device__ __noinline__ void exact_merge(const uint32_t *src, uint32_t *mine, const float *post, int L,
-                                         int nws, int nwd, int TGv, int NT, int sh, uint32_t drop, int s,
-                                         int src_g) {
+__device__ __noinline__ int exact_merge(const uint32_t *src, uint32_t *mine, const float *post, int L, int TGv, int NT,
+                                        uint32_t keep, uint32_t app, int s, int src_g) {
   const float NEG = neg_inf();
   MergeLists<LP> M;
-  M.src = src + (src_g >= 0 ? src_g : 0);
-  M.plane_stride = LP * TGv;
-  M.list_stride = (1 + nws) * M.plane_stride;
+  M.src = src + src_g;
   M.tg = TGv;
-  M.nws = nws; M.nwd = nwd; M.sh = sh; M.s = s; M.drop = drop;
+  M.s = s;
+  M.keep = keep;
+  M.app = app;
   for (int j = 0; j < L; j++) {
     M.st_sc[j] = __uint_as_float(mine[j * NT]);
-    for (int w = 0; w < nwd; w++) M.st_id[j * kMaxIdWords + w] = mine[((1 + w) * LP + j) * NT];
+    M.st_id[j] = mine[(LP + j) * NT];
+    M.st_pt[j] = mine[(2 * LP + j) * NT];
   }
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
@@ -206,20 +241,18 @@ __device__ __noinline__ void exact_merge(const uint32_t *src, uint32_t *mine, co
       const float sc = M.st_sc[0] + wrow[s];
       if (sc > best) { best = sc; bk = s; }
     }
-    if (src_g >= 0) {
-      for (int k = k_first; k <= k_last; k++) {
-        if (k == s) continue;
-        const float sc = M.src_score(k, 0) + wrow[k];
-        if (sc > best) { best = sc; bk = k; }
-      }
+    for (int k = k_first; k <= k_last; k++) {
+      if (k == s) continue;
+      const float sc = M.src_score(k, 0) + wrow[k];
+      if (sc > best) { best = sc; bk = k; }
     }
     mine[0] = __float_as_uint(best);
-    if (bk >= 0) {
-      uint32_t id[kMaxIdWords];
-      M.history(bk, 0, id);
-      for (int w = 0; w < nwd; w++) mine[((1 + w) * LP) * NT] = id[w];
-    }
-    return;
+    if (bk < 0) return 0;
+    uint32_t id, pt;
+    M.identity(bk, 0, id, pt);
+    mine[LP * NT] = id;
+    mine[2 * LP * NT] = pt;
+    return 1;
   }
 
   float hs[8];
@@ -227,12 +260,10 @@ __device__ __noinline__ void exact_merge(const uint32_t *src, uint32_t *mine, co
   HeapRef H{hs, ht};
   int n = 0;
   if (M.st_sc[0] != NEG) { hs[n] = M.st_sc[0] + wrow[s]; ht[n] = (uint32_t)(s << 8); n++; }
-  if (src_g >= 0) {
-    for (int k = k_first; k <= k_last; k++) {
-      if (k == s) continue;
-      const float sc = M.src_score(k, 0);
-      if (sc != NEG) { hs[n] = sc + wrow[k]; ht[n] = (uint32_t)(k << 8); n++; }
-    }
+  for (int k = k_first; k <= k_last; k++) {
+    if (k == s) continue;
+    const float sc = M.src_score(k, 0);
+    if (sc != NEG) { hs[n] = sc + wrow[k]; ht[n] = (uint32_t)(k << 8); n++; }
   }
   heap_make(H, n);
   int l = 0;
@@ -241,17 +272,14 @@ __device__ __noinline__ void exact_merge(const uint32_t *src, uint32_t *mine, co
     n--;
     const float sc = hs[n];
     const int k = (int)(ht[n] >> 8), j = (int)(ht[n] & 255u);
-    uint32_t id[kMaxIdWords];
-    M.history(k, j, id);
+    uint32_t id, pt;
+    M.identity(k, j, id, pt);
     bool dup = false;
-    for (int i = 0; i < l && !dup; i++) {
-      bool same = true;
-      for (int w = 0; w < nwd; w++) same = same && (mine[((1 + w) * LP + i) * NT] == id[w]);
-      dup = same;
-    }
+    for (int i = 0; i < l && !dup; i++) dup = mine[(LP + i) * NT] == id && mine[(2 * LP + i) * NT] == pt;
     if (!dup) {
       mine[l * NT] = __float_as_uint(sc);
-      for (int w = 0; w < nwd; w++) mine[((1 + w) * LP + l) * NT] = id[w];
+      mine[(LP + l) * NT] = id;
+      mine[(2 * LP + l) * NT] = pt;
       l++;
     }
     if (j == L - 1) continue;
@@ -263,107 +291,158 @@ __device__ __noinline__ void exact_merge(const uint32_t *src, uint32_t *mine, co
       heap_push(H, n);
     }
   }
+  const int n_acc = l;
   for (; l < L; l++) mine[l * NT] = __float_as_uint(NEG);
+  return n_acc;
+}
+
+// Row 0 (VCC:706-713): only the start register is reachable, only the stay edge exists and only
+// slot 0 is ever finite.  Eight threads of one CTA per read do it.
+__device__ __forceinline__ void row0_update(const StepArgs &A, const CodeDev &K, uint32_t z, int s) {
+  const unsigned long long off = (unsigned long long)(K.init >> 3) * A.piece_words + (unsigned long long)s * K.LP * 8u + (K.init & 7u);
+  const uint32_t *prv = A.state + row_base(A, K, z, A.t & 1u, 0) + off;
+  uint32_t *cur = A.state + row_base(A, K, z, (A.t + 1u) & 1u, 0) + off;
+  const float w = A.post[(unsigned long long)A.post_blk[z] * 40 + (s >= 4 ? 32 : s * 8) + s];
+  cur[0] = __float_as_uint(__uint_as_float(prv[0]) + w);
+  cur[64u * K.LP] = kRootId;
+  cur[128u * K.LP] = 0u;
+  for (uint32_t l = 1; l < K.L; l++) cur[l * 8u] = 0xff800000u;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Generic step kernel: every width (list slots LP, history words) is a run-time value and every
-// state goes through exact_merge.  Validation mode and fallback for shapes without a
-// specialised kernel.
-//   shared memory: [ post 40 f32 | pad ] [ src tile 8*(1+nws)*LP*TG ] [ own lists (1+nwd)*LP*NT ]
+// Generic step kernel: every state goes through exact_merge; tile width TG and list slots LP as
+// the shape needs.  Validation mode (LVA_FLAG_EXACT_ONLY) and list sizes without a fast kernel.
+//   shared memory: [ post 40 f32 | pad ] [ src tile 3*8*LP*TG ] [ own lists 3*LP*NT ]
 // ---------------------------------------------------------------------------------------------
 template <int LP, int TG>
 __global__ void __launch_bounds__(TG * 8) lva_step_generic(const StepArgs A) {
   constexpr int NT = TG * 8;
   extern __shared__ __align__(128) uint32_t smem[];
   const CodeDev &K = c_code[A.code_slot];
-  const uint32_t a = A.band_a[blockIdx.z];
+  const uint32_t z = blockIdx.z;
+  const uint32_t a = A.band_a[z];
   uint32_t bend = a + A.dev2;
   if (bend > K.nrows) bend = K.nrows;
   if (bend > A.row_hi) bend = A.row_hi;  // a launch may be restricted to rows [row_lo, row_hi)
   const uint32_t p = (a > A.row_lo ? a : A.row_lo) + blockIdx.y;
   if (p >= bend) return;
-
-  const RowDev R = K.row[p];
   const int tid = threadIdx.x;
   const uint32_t tile = blockIdx.x;
-  const Target T = locate_target<TG>(K, R, p, tile, tid);
+  if (p == 0) {
+    if (tile == (K.init / TG) && tid < 8) row0_update(A, K, z, tid);
+    return;
+  }
+  const RowDev R = K.row[p];
+  const int role = tid >= TG * 4;
+  const Target T = locate_target_q<TG>(K, R, tile, tid - role * TG * 4, role);
   if (!__syncthreads_or(T.valid)) return;
 
   const int L = (int)K.L;
-  const int nwd = R.idwords;
-  const int nws = p > 0 ? K.row[p - 1].idwords : 0;
   float *post = reinterpret_cast<float *>(smem);
   uint32_t *src = smem + 64;
-  uint32_t *own = src + 8 * (1 + nws) * LP * TG;
+  uint32_t *own = src + 24 * LP * TG;
+  const uint32_t *prv_src = A.state + row_base(A, K, z, A.t & 1u, p - 1);
+  const uint32_t *prv_own = A.state + row_base(A, K, z, A.t & 1u, p);
+  uint32_t *cur = A.state + row_base(A, K, z, (A.t + 1u) & 1u, p);
 
-  uint32_t *prv = A.state + ((unsigned long long)blockIdx.z * 2 + (A.t & 1u)) * A.slot_words;
-  uint32_t *cur = A.state + ((unsigned long long)blockIdx.z * 2 + ((A.t + 1u) & 1u)) * A.slot_words;
-
-  // ---- stage: posterior block, predecessor tile, own (stay) lists ----
-  if (tid < 10) cp_async16(post + tid * 4, A.post + (unsigned long long)A.post_blk[blockIdx.z] * 40 + tid * 4);
-  if (p > 0) {
-    const RowDev S = K.row[p - 1];
-    const uint32_t first = tile * TG;  // first predecessor conv state of this CTA
-    const uint32_t *g = prv + S.off + (unsigned long long)(first >> 5) * S.tile_words + (first & 31u);
-    const int lines = 8 * (1 + nws) * LP;      // each line: TG consecutive words
-    constexpr int CH = TG / 4;                 // 16-byte chunks per line
-    for (int i = tid; i < lines * CH; i += NT) {
-      const int line = i / CH, ch = i % CH;
-      cp_async16(src + line * TG + ch * 4, g + (unsigned long long)line * 32 + ch * 4);
+  // ---- stage: posterior block, predecessor tile (pieces -> rows of TG words), own (stay) lists ----
+  if (tid < 10) cp_async16(post + tid * 4, A.post + (unsigned long long)A.post_blk[z] * 40 + tid * 4);
+  {
+    constexpr int CH = TG / 4;  // 16-byte chunks per staged row
+    const uint32_t first_piece = tile * (TG / 8);
+    const uint32_t *nid = A.nid + nid_base(A, K, z, A.t & 1u, R.src_nid_slot);
+    const int planes = R.post_boundary ? 2 : 3;
+    for (int i = tid; i < planes * 8 * LP * CH; i += NT) {
+      const int rowi = i / CH, ch = i % CH, plane = rowi / (8 * LP), r_in = rowi % (8 * LP);
+      const uint32_t piece = first_piece + (uint32_t)(ch >> 1);
+      const uint32_t *g = (R.post_boundary && plane == 1)
+                              ? nid + (unsigned long long)piece * (64u * LP) + r_in * 8 + (ch & 1) * 4
+                              : prv_src + (unsigned long long)piece * A.piece_words + (plane * 8 * LP + r_in) * 8 + (ch & 1) * 4;
+      cp_async16(src + rowi * TG + ch * 4, g);
     }
   }
-  const unsigned long long own_base =
-      R.off + (unsigned long long)(T.c >> 5) * R.tile_words + (T.c & 31u) +
-      (unsigned long long)T.s * (1 + nwd) * LP * 32;
-  for (int i = 0; i < (1 + nwd) * LP; i++) cp_async4(own + i * NT + tid, prv + own_base + (unsigned long long)i * 32);
+  const unsigned long long own_off = (unsigned long long)(T.c >> 3) * A.piece_words + (unsigned long long)T.s * LP * 8 + (T.c & 7u);
+  if (T.valid)
+    for (int i = 0; i < 3 * LP; i++)
+      cp_async4(own + i * NT + tid, prv_own + own_off + (unsigned long long)((i / LP) * 8 * LP + (i % LP)) * 8);
   cp_async_wait_all();
   __syncthreads();
-
   if (!T.valid) return;
+
   uint32_t *mine = own + tid;
-  if (p == 0) {  // VCC:706-713: only the stay edge, only slot 0
-    const int row = T.s >= 4 ? 4 : T.s;
-    mine[0] = __float_as_uint(__uint_as_float(mine[0]) + post[row * 8 + T.s]);
-    for (int l = 1; l < L; l++) mine[l * NT] = __float_as_uint(neg_inf());
-  } else {
-    exact_merge<LP>(src, mine, post, L, nws, nwd, TG, NT, R.shift, T.drop, T.s, T.src_g);
+  const uint32_t appv = appended_bits(T.xy, R.shift, R.app) << R.app_pos;
+  const int n_acc = exact_merge<LP>(src, mine, post, L, TG, NT, R.post_boundary ? 0u : 0xffffffffu, appv, T.s, T.src_g);
+  for (int i = 0; i < 3 * LP; i++)
+    if ((i % LP) < L) cur[own_off + (unsigned long long)((i / LP) * 8 * LP + (i % LP)) * 8] = mine[i * NT];
+  if (R.boundary) {  // publish the interned id of every new entry for the row above
+    uint32_t *nidw = A.nid + nid_base(A, K, z, (A.t + 1u) & 1u, R.nid_slot) + (unsigned long long)(T.c >> 3) * (64u * LP) +
+                     (unsigned long long)T.s * LP * 8 + (T.c & 7u);
+    unsigned long long *tab = A.tab + (unsigned long long)z * ((unsigned long long)A.tab_mask + 1ull);
+    for (int l = 0; l < n_acc; l++)
+      nidw[l * 8] = intern_chunk(tab, A.tab_mask, mine[(LP + l) * NT], mine[(2 * LP + l) * NT], A.counters, z);
   }
-  for (int i = 0; i < (1 + nwd) * LP; i++) cur[own_base + (unsigned long long)i * 32] = mine[i * NT];
 }
 
 // ---------------------------------------------------------------------------------------------
 // slot initialisation: every path metric -inf (VCC:611-620), then metric 0 in slot 0 of
 // (row 0, start register, every crf state) of parity buffer 0 (VCC:657-663).
 // ---------------------------------------------------------------------------------------------
-__global__ void lva_fill_neg_inf(uint32_t *state, unsigned long long words) {
+__global__ void lva_fill_u32x4(uint32_t *dst, unsigned long long words, uint32_t v) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 4ull;
   for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 4ull; i < words;
        i += stride) {
-    *reinterpret_cast<uint4 *>(state + i) = make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u);
+    *reinterpret_cast<uint4 *>(dst + i) = make_uint4(v, v, v, v);
   }
 }
 
-__global__ void lva_seed_start(uint32_t *state, unsigned long long slot_words, uint32_t code_slot,
-                               uint32_t n_slots) {
+__global__ void lva_seed_start(uint32_t *state, unsigned long long parity_words, uint32_t piece_words,
+                               uint32_t code_slot, uint32_t n_slots) {
   const CodeDev &K = c_code[code_slot];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots * 8) return;
   const uint32_t slot = i >> 3, s = i & 7;
-  const RowDev R = K.row[0];
-  uint32_t *buf0 = state + (unsigned long long)slot * 2 * slot_words;
-  buf0[R.off + (unsigned long long)(K.init >> 5) * R.tile_words +
-       ((unsigned long long)s * (1 + R.idwords) * K.LP) * 32 + (K.init & 31u)] = 0u;  // 0.0f
+  uint32_t *e = state + (unsigned long long)slot * 2 * parity_words + (unsigned long long)(K.init >> 3) * piece_words +
+                (unsigned long long)s * K.LP * 8u + (K.init & 7u);
+  e[0] = 0u;  // 0.0f
+  e[64u * K.LP] = kRootId;
+  e[128u * K.LP] = 0u;
+}
+
+// A row that enters the band re-uses the window slot of a row that left it long ago: before the
+// step, its metrics are set to -inf in both parity buffers (rows above the band are -inf in the
+// reference, VCC:611-620; states the step never writes -- unreachable bases, pinned register
+// bits -- must read as -inf ever after).
+struct ClearArgs {
+  uint32_t *state;
+  unsigned long long parity_words;
+  uint32_t row_words, piece_words, code_slot;
+  uint16_t row[kMaxSlots];  // per active slot: the row to clear, 0xFFFF = none
+};
+__global__ void lva_clear_rows(const ClearArgs A) {
+  const CodeDev &K = c_code[A.code_slot];
+  const uint32_t z = blockIdx.y;
+  const uint32_t p = A.row[z];
+  if (p == 0xFFFFu) return;
+  const uint32_t metric_words = 64u * K.LP;  // metric plane of one piece, in words
+  const uint32_t per_piece4 = metric_words / 4u;
+  const uint32_t total = (K.nconv >> 3) * per_piece4 * 2u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t parity = i & 1u, j = i >> 1, piece = j / per_piece4, q = j % per_piece4;
+    uint32_t *dst = A.state + ((unsigned long long)z * 2 + parity) * A.parity_words +
+                    (unsigned long long)(p % K.window) * A.row_words + (unsigned long long)piece * A.piece_words + q * 4u;
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // final collection (VCC:806-815): the 8*L entries of (last row, end register, every crf state)
-// of the buffer written by the read's last step, as [slot][crf][slot][1+nw+1] words, and -- when
-// asked -- the CRC-8 / index check the reference's drivers run on every list entry afterwards
-// (helper.decode_list_CRC_index, /root/reference/helper.py:371-388; message framing
-// helper.py:257-264): strip the pad bit, left-pad the bit string to whole bytes, CRC-8
-// (poly 0x07, init 0) of all but the last byte must equal the last byte; the oligo index is the
-// low 12 bits of the first two bytes pushed back through the PRP x -> 1751 x + 2532 mod 4096.
+// of the buffer written by the read's last step -- metric, the message read back through the
+// chain of interned chunks, and -- when asked -- the CRC-8 / index check the reference's drivers
+// run on every list entry afterwards (helper.decode_list_CRC_index,
+// /root/reference/helper.py:371-388; message framing helper.py:257-264): strip the pad bit,
+// left-pad the bit string to whole bytes, CRC-8 (poly 0x07, init 0) of all but the last byte must
+// equal the last byte; the oligo index is the low 12 bits of the first two bytes pushed back
+// through the PRP x -> 1751 x + 2532 mod 4096.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t crc8_step(uint32_t crc, uint32_t byte) {
   crc ^= byte;
@@ -403,33 +482,64 @@ __device__ __forceinline__ uint32_t crc_word_of(const CodeDev &K, const uint32_t
 __global__ void lva_collect_final(const FinalArgs A) {
   const CodeDev &K = c_code[A.code_slot];
   const uint32_t p = K.nrows - 1;
-  const RowDev R = K.row[p];
   const uint32_t per_slot = 8 * K.LP;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n_slots * per_slot) return;
   const uint32_t slot = i / per_slot, e = i % per_slot, s = e / K.LP, j = e % K.LP;
   const ReadDev rd = A.reads[slot];
-  const uint32_t *buf = A.state + ((unsigned long long)slot * 2 + (rd.T & 1u)) * A.slot_words;
-  const unsigned long long base = R.off + (unsigned long long)(K.fin >> 5) * R.tile_words + (K.fin & 31u);
-  const uint32_t planes = 1 + R.idwords;
-  uint32_t v[1 + kMaxIdWords];
-  for (uint32_t w = 0; w < planes; w++) {
-    v[w] = buf[base + ((unsigned long long)(s * planes + w) * K.LP + j) * 32];
-    A.out[(unsigned long long)i * (planes + 1) + w] = v[w];
+  const uint32_t *ent = A.state + ((unsigned long long)slot * 2 + (rd.T & 1u)) * A.parity_words +
+                        (unsigned long long)(p % K.window) * A.row_words + (unsigned long long)(K.fin >> 3) * A.piece_words +
+                        (unsigned long long)(s * K.LP + j) * 8u + (K.fin & 7u);
+  uint32_t *out = A.out + (unsigned long long)i * kFinalWords;
+  const uint32_t metric = ent[0];
+  out[0] = metric;
+  uint32_t hist[8];
+  for (int w = 0; w < 8; w++) hist[w] = 0;
+  if (metric != 0xff800000u && j < K.L) {
+    // message bit b sits at absolute position b: completed chunks first, the partial chunk last
+    uint32_t abs_bits[9];
+    for (int w = 0; w < 9; w++) abs_bits[w] = 0;
+    uint32_t id = ent[64u * K.LP], chunk = ent[128u * K.LP];
+    uint32_t end = K.msg_len, len = K.last_plen;
+    const unsigned long long *tab = A.tab + (unsigned long long)slot * A.tab_slots;
+    for (int k = (int)K.nchunks; k >= 0; k--) {
+      const uint32_t start = end - len;  // this chunk covers [start, end)
+      if (len > 0) {
+        const unsigned long long v = (unsigned long long)(len < 32 ? (chunk & ((1u << len) - 1u)) : chunk) << (start & 31u);
+        abs_bits[start >> 5] |= (uint32_t)v;
+        abs_bits[(start >> 5) + 1] |= (uint32_t)(v >> 32);
+      }
+      if (k == 0) break;
+      const unsigned long long key = tab[id & (A.tab_slots - 1u)];
+      id = (uint32_t)(key >> 32);
+      chunk = (uint32_t)key;
+      end = start;
+      len = K.chunk_len[k - 1];
+    }
+    // history word format of the host tail: bit k = message bit msg_len-1-k
+    for (uint32_t b = 0; b < K.msg_len; b++) {
+      const uint32_t bit = (abs_bits[b >> 5] >> (b & 31u)) & 1u, k = K.msg_len - 1u - b;
+      hist[k >> 5] |= bit << (k & 31u);
+    }
   }
+  for (int w = 0; w < 8; w++) out[1 + w] = hist[w];
   uint32_t crcw = 0;
-  if (A.crc_pad >= 0 && v[0] != 0xff800000u) crcw = crc_word_of(K, v + 1, A.crc_pad);
-  A.out[(unsigned long long)i * (planes + 1) + planes] = crcw;
+  if (A.crc_pad >= 0 && metric != 0xff800000u) crcw = crc_word_of(K, hist, A.crc_pad);
+  out[9] = crcw;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Survivor mode (list size 1): batched traceback.  The step kernels kept metrics only and wrote
-// one 4-bit decision per state and step (lva_step_fast<1,0>); one thread per read walks them back
+// Survivor mode (list size 1): batched traceback.  The step kernel kept metrics only and wrote
+// one 4-bit decision per state and step (lva_step_l1); one thread per read walks them back
 // from the best end state and rebuilds the message from the register bits of every move.
 // The reference's band quirk is followed exactly: a move at step t into the lowest in-band row
 // may read a value that was last written 3, 5, ... steps earlier (rows below the band are not
 // cleared, VCC:667-687), so the walk jumps to the step that actually produced that value.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long l1_word(const CodeDev &K, uint32_t p, uint32_t c, uint32_t s) {
+  return (unsigned long long)p * K.nconv * 8u + (unsigned long long)(c >> 5) * 256u + s * 32u + (c & 31u);
+}
+
 __global__ void lva_traceback(const TraceArgs A) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= A.n_slots) return;
@@ -441,12 +551,9 @@ __global__ void lva_traceback(const TraceArgs A) {
   uint32_t p = K.nrows - 1, c = K.fin;
   int s = -1;
   float best = neg_inf();
-  {
-    const RowDev R = K.row[p];
-    for (int crf = 0; crf < 8; crf++) {  // first strict maximum == stable descending sort, first entry
-      const float sc = __uint_as_float(buf[R.off + (unsigned long long)(c >> 5) * R.tile_words + crf * 32 + (c & 31u)]);
-      if (sc > best) { best = sc; s = crf; }
-    }
+  for (int crf = 0; crf < 8; crf++) {  // first strict maximum == stable descending sort, first entry
+    const float sc = __uint_as_float(buf[l1_word(K, p, c, crf)]);
+    if (sc > best) { best = sc; s = crf; }
   }
   out[0] = __float_as_uint(best);
   out[1] = s >= 0 ? 1u : 0u;

@@ -104,11 +104,41 @@ class ListDecoder:
             raise LvaError(int(status[bad]), f"Too small post matrix (read {bad})")
         return bits, scores, counts, status
 
+    def decode_ranges(self, post, starts, ends, device_ptr: int | None = None, strict=True):
+        """Reads given as block ranges [starts[i], ends[i]) of ONE posterior array (host array `post`, or
+        device memory at `device_ptr`): what helper.truncate_post_file does with a file copy
+        (helper.py:211-224), without moving the posteriors.  -> list of (bits, scores)."""
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        ends = np.ascontiguousarray(ends, dtype=np.uint64)
+        n = starts.size
+        L, M = self.list_size, self.msg_len
+        bits = np.zeros((n, L, M), dtype=np.uint8)
+        scores = np.full((n, L), -np.inf, dtype=np.float32)
+        counts = np.zeros(n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        if n == 0:
+            return []
+        if device_ptr is None:
+            post = np.ascontiguousarray(post, dtype=np.float32)
+            ptr, on_dev = post.ctypes.data, 0
+        else:
+            ptr, on_dev = device_ptr, 1
+        st = self._L.lva_decode_ranges(self._h, ptr, on_dev, starts.ctypes.data, ends.ctypes.data, n, bits.ctypes.data,
+                                       scores.ctypes.data, counts.ctypes.data, status.ctypes.data)
+        if st != 0:
+            raise LvaError(st, self._L.lva_last_error(self._h).decode(errors="replace"))
+        if strict and (status != 0).any():
+            bad = int(np.flatnonzero(status)[0])
+            raise LvaError(int(status[bad]), f"Too small post matrix (read {bad})")
+        return [(bits[i, :counts[i]].copy(), scores[i, :counts[i]].copy()) for i in range(n)]
+
     def decode_with_crc(self, posts: Sequence[np.ndarray], pad: bool, num_oligos: int):
         """decode + helper.decode_list_CRC_index on the GPU: per read (bits, scores, crc_ok[n_i],
         index[n_i], choice) with choice = first entry whose CRC matches and index < num_oligos, or -1."""
         posts = [np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 40) for p in posts]
         n = len(posts)
+        if n == 0:
+            return []
         offsets = np.zeros(n + 1, dtype=np.uint64)
         offsets[1:] = np.cumsum([p.shape[0] for p in posts])
         flat = np.concatenate(posts, axis=0)
