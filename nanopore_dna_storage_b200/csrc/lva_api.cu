@@ -640,6 +640,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *start
     a.code_slot = h->code_slot;
     a.row_lo = 0;
     a.row_hi = k.nrows;
+    { static const char *dbg_env = getenv("LVA_DBG"); a.dbg = dbg_env ? (uint32_t)atoi(dbg_env) : 0u; }
     ClearArgs clr{};
     clr.state = a.state;
     clr.parity_words = h->parity_words;

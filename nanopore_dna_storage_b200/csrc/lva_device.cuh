@@ -85,6 +85,7 @@ struct StepArgs {
   uint32_t tab_mask;              // tab_slots - 1
   uint32_t t, dev2, code_slot;
   uint32_t row_lo, row_hi;        // rows this launch is responsible for
+  uint32_t dbg;                   // developer ablations (LVA_DBG), 0 in production
   uint32_t post_blk[kMaxSlots];   // per active slot: index of the posterior block of this step
   uint16_t band_a[kMaxSlots];     // per active slot: first in-band row of this step (VCC:677-678)
   uint16_t fresh[kMaxSlots];      // per active slot: rows >= fresh enter the band at this step (their window slot holds a recycled row: own list = -inf)

@@ -161,7 +161,7 @@ __device__ __forceinline__ void select_head(const float (&h)[NL], float &best, i
 // overwrites whatever was stored).
 template <int LP, int NL>
 __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL> &V, int L, bool nohist,
-                                           AcceptLog<LP> &log) {
+                                           AcceptLog<LP> &log, uint32_t dbg = 0) {
   constexpr uint32_t GP = 64u * LP;  // words between the planes of a list in HBM
   const float NEG = neg_inf();
   float h[NL];
@@ -201,6 +201,7 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL>
     } else {
       uint32_t m = log.match(csig);
       dup = false;
+      if (dbg & 1u) { dup = m != 0; m = 0; }  // ablation: a signature match counts as a duplicate (WRONG results)
       while (m != 0 && !dup) {
         const uint32_t d = log.desc_at(__ffs(m) - 1);
         m &= m - 1u;
@@ -315,13 +316,29 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
     bulk_g2s(post, A.post + (unsigned long long)A.post_blk[z] * 40, 160u, bar);
     const uint32_t prv_row = ((z * 2u + (A.t & 1u)) * K.window);
     const int src_piece = (int)((prv_row + (p - 1) % K.window) * ppr + tile * 4u);
-    for (uint32_t pl = 0; pl < src_planes; pl++)
-      tensor3d_g2s(src + pl * 8 * LP * TG, &src_map, 0, src_piece, (int)(pl * 8 * LP), bar);
+    if (A.dbg & 4u) {  // ablation: the tile as ONE contiguous bulk copy (wrong shared-memory layout)
+      bulk_g2s(src, A.state + row_base(A, K, z, A.t & 1u, p - 1) + (unsigned long long)tile * 4u * A.piece_words,
+               src_planes * plane_bytes, bar);
+    } else {
+      for (uint32_t pl = 0; pl < src_planes; pl++)
+        tensor3d_g2s(src + pl * 8 * LP * TG, &src_map, 0, src_piece, (int)(pl * 8 * LP), bar);
+    }
     if (R.post_boundary)  // the chain ids of a completed chunk come from the source row's nid plane
       tensor3d_g2s(src + 8 * LP * TG, &nid_map, 0,
                    (int)(((z * 2u + (A.t & 1u)) * K.nid_ring + R.src_nid_slot) * ppr + tile * 4u), 0, bar);
     const int own_piece0 = (int)((prv_row + p % K.window) * ppr);
-    if (!one_bit) {
+    if (A.dbg & 8u) {  // ablation: own lists as contiguous bulk copies (wrong shared-memory layout)
+      const uint32_t *rowp = A.state + row_base(A, K, z, A.t & 1u, p);
+      if (!one_bit) {
+        for (uint32_t w = 0; w < 8; w++)
+          bulk_g2s(own + w * 3 * LP * TG, rowp + (unsigned long long)(((w & 3u) << (K.mem - 5)) + tile) * A.piece_words + (w >> 2) * 3u * LP * TG,
+                   warp_bytes, bar);
+      } else {
+        for (uint32_t w = 0; w < 4; w++)
+          bulk_g2s(own + w * 6 * LP * TG, rowp + (unsigned long long)(((w & 1u) << (K.mem - 4)) + tile * 2u) * A.piece_words + (w >> 1) * 6u * LP * TG,
+                   2u * warp_bytes, bar);
+      }
+    } else if (!one_bit) {
       for (uint32_t w = 0; w < 8; w++)
         tensor5d_g2s(own + w * 3 * LP * TG, &own_map, 0, (int)(4u * (w >> 2)), 0, 0,
                      own_piece0 + (int)(((w & 3u) << (K.mem - 5)) + tile), bar);
@@ -357,6 +374,16 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
   if (!valid) return;
 
   uint32_t *mine = own + pos;
+  if (A.dbg & 2u) {  // ablation: data movement only -- the own list is copied to the new list (WRONG results)
+    if (A.dbg & 16u) { if (mine[0] == 0x12345678u) dst[0] = src[src_g]; return; }  // ... and no stores
+#pragma unroll
+    for (int l = 0; l < LP; l++) {
+      __stcs(dst + l * 8, mine[l * 32]);
+      __stcs(dst + GP + l * 8, mine[(LP + l) * 32] ^ src[src_g + l * 32]);
+      __stcs(dst + 2 * GP + l * 8, mine[(2 * LP + l) * 32]);
+    }
+    return;
+  }
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
   const uint32_t *srcg = src + src_g;
@@ -374,12 +401,12 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
   if (role == 0) {
     ListView<LP, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    n_acc = merge_lists<LP, 8>(dst, V, L, R.nohist != 0, log);
+    n_acc = merge_lists<LP, 8>(dst, V, L, R.nohist != 0, log, A.dbg);
     if (R.boundary && n_acc > 0) publish_ids<LP, 8>(V, log, n_acc, nidw, nid_own, tab, A, z);
   } else {
     ListView<LP, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    n_acc = merge_lists<LP, 2>(dst, V, L, R.nohist != 0, log);
+    n_acc = merge_lists<LP, 2>(dst, V, L, R.nohist != 0, log, A.dbg);
     if (R.boundary && n_acc > 0) publish_ids<LP, 2>(V, log, n_acc, nidw, nid_own, tab, A, z);
   }
   if (n_acc < 0) {  // metrics tie where libstdc++'s heap order could show: redo this state exactly
