@@ -167,7 +167,7 @@ int lva_get_timing(const lva_handle *h, lva_timing *out);
  * Replaces, for a batch of reads, helper.find_barcode_pos_in_post (helper.py:157-209) called for the
  * forward barcodes and for their reverse complements, and the orientation / size rule of the driver
  * (generate_decoded_lists.py:68-83).  helper.truncate_post_file (helper.py:211-224) needs no
- * counterpart: pass [out_start, out_end + 1) as the read's block range to lva_decode_batch.
+ * counterpart: pass [out_start, out_end + 1) as the read's block range to lva_decode_ranges.
  *   basecalls / base_offsets   concatenated basecalls (ACGTN bytes), read i = [base_offsets[i], base_offsets[i+1])
  *   trans / trans_offsets      concatenated flappie .trans tables (flappie.c:278-282: one block index per base)
  *   start_barcode, end_barcode as given to the driver; the RC pair is rc(end), rc(start) (generate_decoded_lists.py:33-34)
@@ -203,6 +203,9 @@ int lva_posteriors_batch(int32_t device, const float *trans, const uint64_t *blo
                          float *out_post);
 int lva_posteriors_batch_device(int32_t device, const float *trans_dev, const uint64_t *block_offsets,
                                 uint32_t n_reads, float *out_post_dev);
+
+/* CUDA devices visible to the process (0 when there is none: there is no CPU path). */
+int lva_device_count(void);
 
 const char *lva_version(void);
 

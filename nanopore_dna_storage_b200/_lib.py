@@ -15,7 +15,7 @@ LVA_DEFAULT_DEVIATION = 0xFFFFFFFF
 LVA_FLAG_EXACT_ONLY = 1
 
 EXPORTS = ["lva_create", "lva_destroy", "lva_last_error", "lva_decode_batch", "lva_decode_batch_device", "lva_decode_batch_crc", "lva_decode_ranges",
-           "lva_trim_batch", "lva_posteriors_batch", "lva_posteriors_batch_device", "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_version"]
+           "lva_trim_batch", "lva_posteriors_batch", "lva_posteriors_batch_device", "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_device_count", "lva_version"]
 
 
 class LvaParams(C.Structure):

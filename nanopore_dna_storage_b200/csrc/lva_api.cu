@@ -249,6 +249,11 @@ extern "C" {
 
 const char *lva_version(void) { return "lva_b200 0.2 (sm_100a)"; }
 
+int lva_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t err_len) {
   auto fail = [&](int st, const std::string &msg) -> lva_handle * {
     if (status) *status = st;

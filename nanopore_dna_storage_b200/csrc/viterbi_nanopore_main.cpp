@@ -15,7 +15,14 @@
 //
 // Extensions (rejected by the reference, so they cannot change its meaning):
 //   --batch-list FILE   decode many reads in one process: each line "infile outfile [rc]"
+//   --post-dir DIR --out-prefix P   decode every DIR/*.post (name order) into P_<i>, the naming of
+//                       the reference's driver loop (generate_decoded_lists.py:85); DIR/<name>.post.rc
+//                       marks a reverse-complement read
+//   --info-file FILE    one line per read of a batch: input, list file, orientation, blocks, entries, status
 //   --device N          CUDA device ordinal (default 0)
+//   --devices LIST      several GPUs of the box ("0-7", "0,2,3", "all"): one worker thread and one
+//                       handle per GPU, reads dealt longest-first, forward / rc reads apart
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -26,6 +33,9 @@
 #include <sstream>
 #include <string>
 #include <vector>
+
+#include <dirent.h>
+#include <thread>
 
 #include "../../include/lva_b200.h"
 
@@ -86,6 +96,8 @@ const Opt kOpts[] = {
     {"help", 'h', kBool, true, "false"},
     // extensions
     {"batch-list", 0, kString, false, ""},    {"device", 0, kU32, true, "0"},
+    {"devices", 0, kString, false, ""},       {"post-dir", 0, kString, false, ""},
+    {"out-prefix", 0, kString, false, ""},    {"info-file", 0, kString, false, ""},
 };
 
 struct Parsed {
@@ -238,79 +250,185 @@ int usage_error(const char *msg) {
   return -1;
 }
 
-struct Job { std::string in, out; bool rc; };
+struct Job {
+  std::string in, out;
+  bool rc = false;
+  uint64_t blocks = 0;   // posterior blocks in the file (work estimate)
+  int status = 0;        // 0 ok, 1 too small a posterior, 2 decode failure
+  uint32_t entries = 0;  // list entries written
+};
 
-int run_decode(const Parsed &P, const std::vector<Job> &jobs, bool any_rc_flag) {
-  const uint32_t msg_len = (uint32_t)P.num.at("msg-len");
-  const std::string marker = P.text.at("sync-marker");
-  (void)any_rc_flag;
-  int rc_all = 0;
-  for (int pass = 0; pass < 2; pass++) {  // forward reads, then reverse-complement reads
-    std::vector<size_t> idx;
-    for (size_t i = 0; i < jobs.size(); i++) if (jobs[i].rc == (pass == 1)) idx.push_back(i);
-    if (idx.empty()) continue;
-    lva_params prm{};
-    prm.mem_conv = (uint32_t)P.num.at("mem-conv");
-    prm.rate = (uint32_t)P.num.at("rate");
-    prm.msg_len = msg_len;
-    prm.list_size = (uint32_t)P.num.at("list-size");
-    prm.max_deviation = P.n("max-deviation") ? (uint32_t)P.num.at("max-deviation") : LVA_DEFAULT_DEVIATION;
-    prm.rc = pass;
-    prm.sync_marker = marker.c_str();
-    prm.sync_period = P.n("sync-period") ? (uint32_t)P.num.at("sync-period") : 0;
-    prm.device = (int32_t)P.num.at("device");
-    int st = 0;
-    char err[256] = {0};
-    lva_handle *h = lva_create(&prm, &st, err, sizeof err);
-    if (!h) {
-      if (st >= LVA_ERR_MEM_CONV && st <= LVA_ERR_MARKER_CHAR) {  // set_conv_params failures (VCC:211-214)
-        std::cout << err;
-        std::cout << kHelp << "\n";
-        return -1;
-      }
-      if (st == LVA_ERR_TOO_MANY_STATES || st == LVA_ERR_MSG_TOO_LONG) die_like_uncaught("std::runtime_error", err);
-      fprintf(stderr, "viterbi_nanopore: %s\n", err);
-      return 1;
-    }
+lva_params decode_params(const Parsed &P, const std::string &marker, int rc, int device) {
+  lva_params prm{};
+  prm.mem_conv = (uint32_t)P.num.at("mem-conv");
+  prm.rate = (uint32_t)P.num.at("rate");
+  prm.msg_len = (uint32_t)P.num.at("msg-len");
+  prm.list_size = (uint32_t)P.num.at("list-size");
+  prm.max_deviation = P.n("max-deviation") ? (uint32_t)P.num.at("max-deviation") : LVA_DEFAULT_DEVIATION;
+  prm.rc = rc;
+  prm.sync_marker = marker.c_str();
+  prm.sync_period = P.n("sync-period") ? (uint32_t)P.num.at("sync-period") : 0;
+  prm.device = device;
+  return prm;
+}
+
+// One GPU's share of a batch: the reads of one orientation, decoded in chunks of a few slot-fulls
+// through ONE handle (tables, state memory and chain tables are set up once per handle).
+// Posterior files are read by the worker itself, so the GPUs of a box also read in parallel.
+bool decode_on_device(lva_handle *h, uint32_t msg_len, uint32_t L, std::vector<Job> &jobs, const std::vector<size_t> &mine,
+                      std::string &err) {
+  const size_t chunk_reads = std::max<size_t>(64, 4 * (size_t)lva_slots(h));
+  const uint64_t chunk_blocks = (uint64_t)1 << 22;  // 640 MB of posteriors per call at most
+  size_t at = 0;
+  while (at < mine.size()) {
     std::vector<float> post;
     std::vector<uint64_t> offs(1, 0);
-    for (size_t i : idx) {
-      std::vector<float> f = read_posteriors(jobs[i].in);
+    size_t n = 0;
+    while (at + n < mine.size() && n < chunk_reads && (n == 0 || offs.back() + jobs[mine[at + n]].blocks <= chunk_blocks)) {
+      std::vector<float> f = read_posteriors(jobs[mine[at + n]].in);
       post.insert(post.end(), f.begin(), f.end());
       offs.push_back(post.size() / 40);
+      n++;
     }
-    const uint32_t n = (uint32_t)idx.size(), L = prm.list_size;
-    std::vector<uint8_t> bits((size_t)n * L * msg_len);
+    std::vector<uint8_t> bits(n * L * msg_len);
     std::vector<uint32_t> counts(n);
     std::vector<int32_t> status(n);
     if (post.empty()) post.push_back(0.f);
-    st = lva_decode_batch(h, post.data(), offs.data(), n, bits.data(), nullptr, counts.data(), status.data());
+    const int st = lva_decode_batch(h, post.data(), offs.data(), (uint32_t)n, bits.data(), nullptr, counts.data(), status.data());
     if (st != LVA_OK) {
-      fprintf(stderr, "viterbi_nanopore: decode failed: %s\n", lva_last_error(h));
-      lva_destroy(h);
-      return 1;
+      err = lva_last_error(h);
+      for (size_t r = 0; r < n; r++) jobs[mine[at + r]].status = 2;
+      return false;
     }
-    for (uint32_t r = 0; r < n; r++) {
-      if (status[r] == LVA_ERR_POST_TOO_SMALL) {
-        if (jobs.size() == 1) {
-          lva_destroy(h);
-          die_like_uncaught("std::runtime_error", "Too small post matrix");  // VCC:600-601
-        }
-        fprintf(stderr, "viterbi_nanopore: %s: Too small post matrix\n", jobs[idx[r]].in.c_str());
-        rc_all = 1;
-        continue;
-      }
-      std::ofstream fout(jobs[idx[r]].out);  // VCC:248-253
+    for (size_t r = 0; r < n; r++) {
+      Job &j = jobs[mine[at + r]];
+      if (status[r] == LVA_ERR_POST_TOO_SMALL) { j.status = 1; continue; }
+      std::ofstream fout(j.out);  // VCC:248-253
       for (uint32_t e = 0; e < counts[r]; e++) {
-        const uint8_t *b = &bits[((size_t)r * L + e) * msg_len];
+        const uint8_t *b = &bits[(r * L + e) * msg_len];
         std::string line(msg_len, '0');
         for (uint32_t k = 0; k < msg_len; k++) line[k] = b[k] ? '1' : '0';
         fout << line << "\n";
       }
+      j.entries = counts[r];
     }
-    lva_destroy(h);
+    at += n;
   }
+  return true;
+}
+
+// Multi-GPU host of the batch extension: reads are independent, so they are
+// dealt longest-first onto the least-loaded GPU, forward and reverse-complement reads apart (they
+// need different code tables, i.e. different handles); one worker thread per GPU decodes its share
+// and writes the list files by read; nothing is exchanged between GPUs.
+int run_decode(const Parsed &P, std::vector<Job> &jobs, const std::vector<int> &devices) {
+  const uint32_t msg_len = (uint32_t)P.num.at("msg-len"), L = (uint32_t)P.num.at("list-size");
+  const std::string marker = P.text.at("sync-marker");
+  for (Job &j : jobs) {
+    std::ifstream f(j.in, std::ios::binary | std::ios::ate);
+    j.blocks = f ? ((uint64_t)std::max<std::streamoff>(f.tellg(), 0) + 159) / 160 : 0;
+  }
+  const size_t ndev = devices.size();
+  std::vector<std::vector<size_t>> share[2];  // [orientation][device] -> job indices
+  for (int pass = 0; pass < 2; pass++) {
+    share[pass].assign(ndev, {});
+    std::vector<size_t> idx;
+    for (size_t i = 0; i < jobs.size(); i++) if (jobs[i].rc == (pass == 1)) idx.push_back(i);
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return jobs[x].blocks > jobs[y].blocks; });
+    std::vector<uint64_t> load(ndev, 0);
+    for (size_t i : idx) {
+      const size_t d = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+      share[pass][d].push_back(i);
+      load[d] += std::max<uint64_t>(jobs[i].blocks, 1);
+    }
+  }
+  // The first handle is made on this thread so that parameter errors surface exactly like the
+  // reference's set_conv_params failures (text + usage on stdout, return -1; VCC:211-214).
+  lva_handle *first = nullptr;
+  int first_pass = -1;
+  size_t first_dev = 0;
+  for (int pass = 0; pass < 2 && !first; pass++)
+    for (size_t d = 0; d < ndev && !first; d++)
+      if (!share[pass][d].empty()) {
+        const lva_params prm = decode_params(P, marker, pass, devices[d]);
+        int st = 0;
+        char err[256] = {0};
+        first = lva_create(&prm, &st, err, sizeof err);
+        if (!first) {
+          if (st >= LVA_ERR_MEM_CONV && st <= LVA_ERR_MARKER_CHAR) {
+            std::cout << err;
+            std::cout << kHelp << "\n";
+            return -1;
+          }
+          if (st == LVA_ERR_TOO_MANY_STATES || st == LVA_ERR_MSG_TOO_LONG) die_like_uncaught("std::runtime_error", err);
+          fprintf(stderr, "viterbi_nanopore: %s\n", err);
+          return 1;
+        }
+        first_pass = pass;
+        first_dev = d;
+      }
+  if (!first) return 0;  // nothing to decode
+  std::vector<std::string> errors(ndev);
+  auto worker = [&](size_t d) {
+    for (int pass = 0; pass < 2; pass++) {
+      if (share[pass][d].empty()) continue;
+      lva_handle *h = (pass == first_pass && d == first_dev) ? first : nullptr;
+      if (!h) {
+        const lva_params prm = decode_params(P, marker, pass, devices[d]);
+        int st = 0;
+        char err[256] = {0};
+        h = lva_create(&prm, &st, err, sizeof err);
+        if (!h) {
+          errors[d] = err;
+          for (size_t i : share[pass][d]) jobs[i].status = 2;
+          continue;
+        }
+      }
+      std::string e;
+      if (!decode_on_device(h, msg_len, L, jobs, share[pass][d], e)) errors[d] = e;
+      lva_destroy(h);
+    }
+  };
+  if (ndev == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < ndev; d++) th.emplace_back(worker, d);
+    for (auto &t : th) t.join();
+  }
+  int rc_all = 0;
+  for (size_t d = 0; d < ndev; d++)
+    if (!errors[d].empty()) {
+      fprintf(stderr, "viterbi_nanopore: device %d: decode failed: %s\n", devices[d], errors[d].c_str());
+      rc_all = 1;
+    }
+  for (const Job &j : jobs)
+    if (j.status == 1) {
+      if (jobs.size() == 1) die_like_uncaught("std::runtime_error", "Too small post matrix");  // VCC:600-601
+      fprintf(stderr, "viterbi_nanopore: %s: Too small post matrix\n", j.in.c_str());
+      rc_all = 1;
+    }
   return rc_all;
+}
+
+// "0-3", "0,2,5", "all" -> device ordinals (extension --devices)
+std::vector<int> parse_devices(const std::string &spec) {
+  std::vector<int> out;
+  if (spec == "all") {
+    for (int d = 0; d < lva_device_count(); d++) out.push_back(d);
+    return out;
+  }
+  std::stringstream ss(spec);
+  std::string tok;
+  while (std::getline(ss, tok, ',')) {
+    if (tok.empty()) continue;
+    const size_t dash = tok.find('-');
+    try {
+      if (dash == std::string::npos) out.push_back(std::stoi(tok));
+      else for (int d = std::stoi(tok.substr(0, dash)); d <= std::stoi(tok.substr(dash + 1)); d++) out.push_back(d);
+    } catch (...) { out.clear(); return out; }
+  }
+  return out;
 }
 
 int run_encode(const Parsed &P) {
@@ -362,8 +480,10 @@ int main(int argc, char **argv) {
     std::cout << kHelp << "\n";
     return 0;
   }
-  const bool batch = P.n("batch-list") > 0;
-  if (!P.n("mode") || (!batch && (!P.n("infile") || !P.n("outfile")))) return usage_error("Invalid options.\n");
+  const bool dir_mode = P.n("post-dir") > 0;
+  const bool batch = P.n("batch-list") > 0 || dir_mode;
+  if (!P.n("mode") || (!batch && (!P.n("infile") || !P.n("outfile"))) || (dir_mode && !P.n("out-prefix")))
+    return usage_error("Invalid options.\n");
   const std::string mode = P.text.at("mode");
   if (mode != "encode" && mode != "decode") return usage_error("Invalid mode.\n");
   if (!P.n("mem-conv")) return usage_error("Memory of convolutional code not specified.\n");
@@ -377,7 +497,30 @@ int main(int argc, char **argv) {
     return run_encode(P);
   }
   std::vector<Job> jobs;
-  if (batch) {
+  if (dir_mode) {
+    // every *.post of a directory, in name order, to <out-prefix>_<i> -- the naming of the reference's
+    // driver loop (generate_decoded_lists.py:85); a file <name>.rc beside a posterior marks a
+    // reverse-complement read
+    std::vector<std::string> names;
+    if (DIR *d = opendir(P.text.at("post-dir").c_str())) {
+      while (dirent *e = readdir(d)) {
+        const std::string n = e->d_name;
+        if (n.size() > 5 && n.compare(n.size() - 5, 5, ".post") == 0) names.push_back(n);
+      }
+      closedir(d);
+    } else {
+      fprintf(stderr, "viterbi_nanopore: cannot open directory %s\n", P.text.at("post-dir").c_str());
+      return 1;
+    }
+    std::sort(names.begin(), names.end());
+    for (size_t i = 0; i < names.size(); i++) {
+      Job j;
+      j.in = P.text.at("post-dir") + "/" + names[i];
+      j.out = P.text.at("out-prefix") + "_" + std::to_string(i);
+      j.rc = rc_flag || std::ifstream(j.in + ".rc").good();
+      jobs.push_back(j);
+    }
+  } else if (batch) {
     std::ifstream fl(P.text.at("batch-list"));
     std::string line;
     while (std::getline(fl, line)) {
@@ -390,7 +533,25 @@ int main(int argc, char **argv) {
       jobs.push_back(j);
     }
   } else {
-    jobs.push_back(Job{P.text.at("infile"), P.text.at("outfile"), rc_flag});
+    Job j;
+    j.in = P.text.at("infile");
+    j.out = P.text.at("outfile");
+    j.rc = rc_flag;
+    jobs.push_back(j);
   }
-  return run_decode(P, jobs, rc_flag);
+  std::vector<int> devices;
+  if (P.n("devices")) {
+    devices = parse_devices(P.text.at("devices"));
+    if (devices.empty()) { fprintf(stderr, "viterbi_nanopore: bad --devices list\n"); return 1; }
+  } else {
+    devices.push_back((int)P.num.at("device"));
+  }
+  const int rc = run_decode(P, jobs, devices);
+  if (P.n("info-file")) {  // one line per read: input, list file, orientation, blocks, entries, status
+    std::ofstream fi(P.text.at("info-file"));
+    for (const Job &j : jobs)
+      fi << j.in << "\t" << j.out << "\t" << (j.rc ? "rc" : "fwd") << "\t" << j.blocks << "\t" << j.entries << "\t"
+         << (j.status == 0 ? "ok" : j.status == 1 ? "too_small" : "failed") << "\n";
+  }
+  return rc;
 }

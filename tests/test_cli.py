@@ -120,6 +120,53 @@ def test_decode_cli_is_a_drop_in(tmp_path):
 
 
 @pytest.mark.gpu
+def test_batch_manifest_orientations_devices_and_directory_mode(tmp_path, oracle):
+    """The batch host of the CLI: a manifest mixing forward and reverse-complement reads (third column),
+    --devices (every GPU of the box; one worker thread and one handle per GPU and orientation), the
+    directory mode with the reference driver's <prefix>_<i> naming (generate_decoded_lists.py:85) and the
+    per-read info file.  Every list file is compared with the oracle."""
+    import torch
+    w = synth.Workload("cli", 6, 5, 40, 4, 20, sub=0.01, dele=0.01, ins=0.005, seed=951, rc_fraction=0.5)
+    reads = [synth.make_read(w, i) for i in range(9)]
+    assert any(r.rc for r in reads) and not all(r.rc for r in reads)
+    d = tmp_path / "posts"
+    d.mkdir()
+    lines = []
+    for i, r in enumerate(reads):
+        p = d / f"read_{i:03d}.post"
+        r.post.tofile(p)
+        if r.rc:
+            (d / f"read_{i:03d}.post.rc").write_text("")
+        lines.append(f"{p} {tmp_path / f'm_{i}'}" + (" rc" if r.rc else ""))
+    (tmp_path / "batch.txt").write_text("\n".join(lines) + "\n")
+    want = []
+    for r in reads:
+        st, bits, _ = oracle.oracle_decode(r.post, 6, 5, 40, 4, 20, r.rc)
+        want.append("".join("".join(map(str, b)) + "\n" for b in bits))
+    common = ["-m", "decode", "--mem-conv", "6", "--msg-len", "40", "-l", "4", "-r", "5", "--max-deviation", "20"]
+    ngpu = torch.cuda.device_count()
+    for devs in (["--device", "0"], ["--devices", "all"], ["--devices", f"0-{ngpu - 1}"]):
+        for f in tmp_path.glob("m_*"):
+            f.unlink()
+        rc, out, err = run(OURS, common + ["--batch-list", str(tmp_path / "batch.txt")] + devs, tmp_path)
+        assert rc == 0, err
+        for i in range(len(reads)):
+            assert (tmp_path / f"m_{i}").read_text() == want[i], (devs, i)
+    rc, out, err = run(OURS, common + ["--post-dir", str(d), "--out-prefix", str(tmp_path / "list"), "--info-file",
+                                       str(tmp_path / "info.txt"), "--devices", "all"], tmp_path)
+    assert rc == 0, err
+    info = (tmp_path / "info.txt").read_text().splitlines()
+    assert len(info) == len(reads)
+    for i, r in enumerate(reads):
+        assert (tmp_path / f"list_{i}").read_text() == want[i]
+        cols = info[i].split("\t")
+        assert cols[0].endswith(f"read_{i:03d}.post") and cols[2] == ("rc" if r.rc else "fwd")
+        assert int(cols[3]) == r.post.shape[0] and int(cols[4]) == want[i].count("\n") and cols[5] == "ok"
+    rc, out, err = run(OURS, common + ["--batch-list", str(tmp_path / "batch.txt"), "--devices", "9-3"], tmp_path)
+    assert rc == 1 and b"--devices" in err
+
+
+@pytest.mark.gpu
 def test_batch_list_extension(tmp_path, oracle):
     w = synth.Workload("cli", 6, 1, 40, 4, 20, sub=0.01, dele=0.01, ins=0.005, seed=950)
     lines, reads = [], []

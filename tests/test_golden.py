@@ -10,7 +10,9 @@ import pytest
 
 from nanopore_dna_storage_b200 import synth
 
-GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_lists.json")))["cases"]
+GOLD = []
+for _name in ("reference_lists.json", "reference_lists_r2.json"):  # make_golden.py, make_golden_r2.py
+    GOLD += json.load(open(os.path.join(os.path.dirname(__file__), "golden", _name)))["cases"]
 
 
 def _regen(case):
@@ -26,7 +28,10 @@ def _bits(lists, msg_len):
     return np.array([[int(c) for c in s] for s in lists], dtype=np.uint8).reshape(len(lists), msg_len)
 
 
-SMALL = [c for c in GOLD if c["workload"]["mem_conv"] <= 8]
+# CPU suite: every small-code case up to list size 16, plus one L = 32 and one L = 64 read (the oracle
+# needs about half a minute for those)
+SMALL = [c for c in GOLD if c["workload"]["mem_conv"] <= 8 and
+         (c["workload"]["list_size"] <= 16 or (c["workload"]["list_size"] == 32 and c["read"] == 0) or c["rc"])]
 
 
 @pytest.mark.parametrize("case", SMALL, ids=[f"{c['name']}#{c['read']}" for c in SMALL])
@@ -40,7 +45,8 @@ def test_oracle_reproduces_reference_lists(oracle, case):
 
 @pytest.mark.gpu
 def test_gpu_reproduces_reference_lists():
-    """Every golden case, including the full-size C2 / C5 / m=14 reads, through the C ABI."""
+    """Every golden case through the C ABI: the full-size C2 bench reads (incl. beta = 3 hard reads and
+    lengths that are multiples of 29), C3 at msg_len 100 and 180, C5 in both orientations, L = 32 / 64."""
     from nanopore_dna_storage_b200.decoder import ListDecoder
     groups = {}
     for c in GOLD:

@@ -73,6 +73,27 @@ def test_quantised_posteriors_force_ties(oracle, exact_only):
             assert tm["exact_fallbacks"] > 0, "quantised posteriors produced no tie fallback"
 
 
+@pytest.mark.parametrize("mem,rate,msg_len,L", [(6, 1, 40, 4), (6, 5, 40, 8), (8, 3, 41, 3)])
+def test_flat_posteriors_tie_everywhere(oracle, mem, rate, msg_len, L):
+    """Every transition equally likely: ALL metrics of a step tie, three-way ties with duplicates included
+    (a copy dropped by the fast merge may be the entry libstdc++'s heap pops first).  The list is then
+    decided by heap order alone; the fast path must notice and hand every such state to the exact merge."""
+    T = 3 * (msg_len + mem) + 7
+    post = np.full((T, 40), np.float32(np.log(1.0 / 40.0)), dtype=np.float32)
+    post2 = post.copy()
+    post2[::3, 5] += np.float32(0.5)   # a few equal bumps: ties between paths of different shape
+    post2[1::4, 33] += np.float32(0.5)
+    for rc in (False, True):
+        with ListDecoder(mem, rate, msg_len, L, 20, rc=rc) as dec:
+            got = dec.decode([post, post2])
+            tm = dec.timing()
+        assert tm["exact_fallbacks"] > 0
+        for pp, (bits, scores) in zip((post, post2), got):
+            st, obits, oscores = oracle.oracle_decode(pp, mem, rate, msg_len, L, 20, rc)
+            assert st == 0 and bits.shape == obits.shape and np.array_equal(bits, obits)
+            assert np.array_equal(scores.view(np.uint32), oscores.view(np.uint32))
+
+
 def test_more_reads_than_slots(oracle):
     w = synth.Workload("t", 6, 1, 40, 4, 20, sub=0.01, dele=0.01, ins=0.005, seed=7001)
     _compare(oracle, w, 11, exact_only=False, max_slots=4, tag="11 reads in 4 slots")

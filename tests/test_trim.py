@@ -122,8 +122,17 @@ def test_gpu_trim_then_decode_uses_block_ranges():
     keep, starts, ends = trim.truncated_block_offsets(block_offsets, trims)
     assert keep == [0, 1, 2]
     flat = np.concatenate(padded)
+    import torch
     with ListDecoder(w.mem_conv, w.rate, w.msg_len, w.list_size, w.max_deviation, device=0) as dec:
         want = dec.decode([r.post for r in reads])
-        got = dec.decode([flat[int(s):int(e)] for s, e in zip(starts, ends)])
-    for (wb, ws), (gb, gs) in zip(want, got):
+        got = dec.decode_ranges(flat, starts, ends)                       # lva_decode_ranges, host posteriors
+        dev = torch.from_numpy(flat).cuda()
+        got_dev = dec.decode_ranges(None, starts, ends, device_ptr=dev.data_ptr())  # ... posteriors left in HBM
+        # ranges may come in any order and overlap
+        perm = [2, 0, 1, 0]
+        got_perm = dec.decode_ranges(flat, starts[perm], ends[perm])
+    for (wb, ws), (gb, gs), (db, ds) in zip(want, got, got_dev):
         assert np.array_equal(wb, gb) and np.array_equal(ws.view(np.uint32), gs.view(np.uint32))
+        assert np.array_equal(wb, db) and np.array_equal(ws.view(np.uint32), ds.view(np.uint32))
+    for k, (gb, gs) in zip(perm, got_perm):
+        assert np.array_equal(want[k][0], gb) and np.array_equal(want[k][1].view(np.uint32), gs.view(np.uint32))
