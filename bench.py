@@ -9,8 +9,17 @@ A "step" is one pass of the hot path over one batch of synthetic reads of the wo
 `value`  : reads/s with the posteriors already resident in HBM (lva_decode_batch_device).
 `e2e`    : reads/s through the reference-facing C ABI call with HOST buffers (lva_decode_batch):
            H2D of the posteriors and D2H of the candidate lists are inside the timed region.
-Multi-GPU: one process per GPU (torchrun), every rank decodes its own reads (weak scaling, no
-data-path collective); time = max over ranks.
+Multi-GPU: one process per GPU (torchrun); the global read set is dealt to the ranks by the
+product's own length-balanced plan (nanopore_dna_storage_b200/sharding.py), every rank decodes its
+share (weak scaling: reads per GPU fixed, no data-path collective); time = max over ranks.
+
+Outside the timed region the decoded lists of the batch are compared with what the UNMODIFIED
+reference produced for the same reads: the committed fixtures (tests/golden/reference_lists_r2.json,
+reads 0..15 of this workload) and a bounded live CPU sample (`cpu_baseline`).
+
+Reference arm: K distinct reads of the same batch, throughput mode = as many
+single-read processes as the host has cores, each `-t 1` (when K < cores the spare cores go to the
+processes as OpenMP threads); a latency-mode figure (one process, all cores) is reported beside it.
 """
 from __future__ import annotations
 
@@ -19,6 +28,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -28,6 +38,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from nanopore_dna_storage_b200 import synth  # noqa: E402
+
+ISSUE_PEAK_THREAD_INSTR = 148 * 4 * 32  # per clock; x sm_max_mhz = thread-instructions/s
 
 
 def parse():
@@ -40,7 +52,7 @@ def parse():
     ap.add_argument("--reads-per-step", type=int, default=0, help="per GPU; 0 = one full set of slots")
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-reads", type=int, default=1, help="reads in the CPU baseline sample")
+    ap.add_argument("--cpu-reads", type=int, default=2, help="reads of the batch the live CPU sample decodes")
     return ap.parse_args()
 
 
@@ -88,111 +100,193 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_peak_hbm():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+def measured_peaks():
     try:
-        with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return 6650.0, 1965.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """Per-launch DRAM traffic of the dominant kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
+def committed_json(name):
     try:
-        with open(p) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             return json.load(f)
     except Exception:
         return None
 
 
-def ncu_pipes():
-    """Issue / pipe utilisation of the dominant kernel from the committed ncu capture, if any."""
+def golden_lists(w: synth.Workload):
+    """{read index: [list lines]} of the committed reference fixtures made from exactly this workload."""
+    out = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "pipes.json")) as f:
-            return json.load(f)
+        cases = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_lists_r2.json")))["cases"]
     except Exception:
-        return None
+        return out
+    for c in cases:
+        k = c["workload"]
+        if (k["mem_conv"], k["rate"], k["msg_len"], k["list_size"], k["max_deviation"], k["seed"]) == \
+                (w.mem_conv, w.rate, w.msg_len, w.list_size, w.max_deviation, w.seed) and \
+                abs(k.get("rc_fraction", 0.0) - w.rc_fraction) < 1e-9:
+            out[c["read"]] = (c["lists"], c["rc"])
+    return out
 
 
-def cpu_reference_run(w: synth.Workload, reads, threads: int):
-    """Time the reference's own decoder (oracle/_ref, unmodified sources compiled in place) on a
-    bounded sample; falls back to the oracle port if the compiled reference is absent."""
+def lines_of(bits: np.ndarray):
+    return ["".join(map(str, b.tolist())) for b in bits]
+
+
+def workload_config(args, w):
+    return {"workload": f"{w.name} max_deviation={w.max_deviation} (BASELINE.json configs[1])"
+            if args.workload == "C2" else w.name,
+            "mem_conv": w.mem_conv, "rate": w.rate, "msg_len": w.msg_len, "list_size": w.list_size,
+            "max_deviation": w.max_deviation, "rc_fraction": w.rc_fraction,
+            "channel": {"sub": w.sub, "del": w.dele, "ins": w.ins}, "sigma": w.sigma, "betas": list(w.betas)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference CLI (oracle/_ref/viterbi_nanopore.out, compiled in place from
+# /root/reference by oracle/Makefile) on .post files, as its own drivers call it
+# ---------------------------------------------------------------------------------------------------
+def ref_cli_decode_many(w, reads, procs: int, threads: int, tmp: str):
+    """Decode `reads` with `procs` concurrent reference processes of `threads` OpenMP threads each.
+    -> (wall seconds, {read index: list lines})"""
     from oracle import binding as ob
-    kind = "reference" if ob.have_ref() else "port"
-    t0 = time.perf_counter()
+    exe = ob.REF_EXE
+    jobs = []
     for r in reads:
-        if kind == "reference":
-            st, _ = ob.ref_decode(r.post, w.mem_conv, w.rate, w.msg_len, w.list_size, w.max_deviation, r.rc,
-                                  num_thr=threads)
+        pin, pout = os.path.join(tmp, f"r{r.index}.post"), os.path.join(tmp, f"r{r.index}.dec")
+        r.post.tofile(pin)
+        jobs.append((r, [exe, "-m", "decode", "-i", pin, "-o", pout, "--msg-len", str(w.msg_len), "-l", str(w.list_size),
+                         "-t", str(threads), "--mem-conv", str(w.mem_conv), "--rc" if r.rc else "", "--max-deviation",
+                         str(w.max_deviation), "-r", str(w.rate)], pout))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    t0 = time.perf_counter()
+    running, it, out = [], iter(jobs), {}
+    while True:
+        while len(running) < procs:
+            j = next(it, None)
+            if j is None:
+                break
+            running.append((j, subprocess.Popen(j[1], stdout=subprocess.DEVNULL, env=env)))
+        if not running:
+            break
+        for k, (j, p) in enumerate(running):
+            if p.poll() is not None:
+                assert p.returncode == 0, f"reference decoder failed on read {j[0].index}"
+                with open(j[2]) as f:
+                    out[j[0].index] = f.read().split()
+                running.pop(k)
+                break
         else:
-            st, _, _ = ob.oracle_decode(r.post, w.mem_conv, w.rate, w.msg_len, w.list_size, w.max_deviation, r.rc,
-                                        num_thr=threads)
+            time.sleep(0.05)
+    return time.perf_counter() - t0, out
+
+
+def oracle_port_decode_many(w, reads, threads):
+    from oracle import binding as ob
+    t0 = time.perf_counter()
+    out = {}
+    for r in reads:
+        st, bits, _ = ob.oracle_decode(r.post, w.mem_conv, w.rate, w.msg_len, w.list_size, w.max_deviation, r.rc,
+                                       num_thr=threads)
         assert st == 0
-    dt = time.perf_counter() - t0
-    return kind, len(reads) / dt, dt
+        out[r.index] = lines_of(bits)
+    return time.perf_counter() - t0, out
 
 
+def reference_arm(args, w, cfg):
+    from oracle import binding as ob
+    cores = os.cpu_count() or 1
+    K = max(1, args.steps)
+    reads = synth.make_reads(w, K, start=0)  # the first K reads of rank 0's GPU batch
+    kind = "reference" if ob.have_ref() else "port"
+    gold = golden_lists(w)
+    with tempfile.TemporaryDirectory() as tmp:
+        if kind == "reference":
+            # throughput mode: waves of single-read processes; spare cores become OpenMP threads of the processes
+            t_all, lists, waves, left = 0.0, {}, [], list(reads)
+            while left:
+                procs = min(len(left), cores)
+                thr = max(1, cores // procs)
+                dt, out = ref_cli_decode_many(w, left[:procs], procs, thr, tmp)
+                waves.append({"processes": procs, "threads_each": thr, "seconds": round(dt, 1)})
+                t_all += dt
+                lists.update(out)
+                left = left[procs:]
+            # latency mode beside it: one process, every core, one read
+            dt_lat, out_lat = ref_cli_decode_many(w, reads[:1], 1, cores, tmp)
+            assert out_lat[reads[0].index] == lists[reads[0].index], "reference lists depend on -t"
+            latency = {"value": 1.0 / dt_lat, "unit": "reads/s", "sample": f"1 read, one process -t {cores}, {dt_lat:.1f} s"}
+            sample = (f"{K} distinct reads (indices 0..{K - 1} of the GPU batch), throughput mode: "
+                      + "; ".join(f"{x['processes']} processes x -t {x['threads_each']} ({x['seconds']} s)" for x in waves))
+        else:
+            t_all, lists = oracle_port_decode_many(w, reads, cores)
+            latency, sample = None, f"{K} distinct reads, oracle port, one process -t {cores}"
+    checked = 0
+    for r in reads:
+        if r.index in gold:
+            assert lists[r.index] == gold[r.index][0], f"reference arm disagrees with the committed fixture of read {r.index}"
+            checked += 1
+    value = K / t_all
+    print(json.dumps({"impl": "reference", "metric": "reads decoded/s", "value": value, "unit": "reads/s",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * t_all / K, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                      "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind, "sample": sample},
+                      "latency_mode": latency, "reads_checked_against_fixtures": checked,
+                      "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = synth.workloads()[args.workload]
-    cfg = {"workload": f"{w.name} max_deviation={w.max_deviation} (BASELINE.json configs[1])"
-           if args.workload == "C2" else w.name,
-           "mem_conv": w.mem_conv, "rate": w.rate, "msg_len": w.msg_len, "list_size": w.list_size,
-           "max_deviation": w.max_deviation,
-           "channel": {"sub": w.sub, "del": w.dele, "ins": w.ins}, "sigma": w.sigma, "betas": list(w.betas)}
-    threads = os.cpu_count() or 1
+    cfg = workload_config(args, w)
+    cores = os.cpu_count() or 1
 
-    # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
-        if rank != 0:
-            return
-        reads = synth.make_reads(w, max(1, args.cpu_reads), start=10_000_000)
-        for _ in range(min(args.warmup, 1)):
-            pass  # a warm-up decode would cost as much as a timed one; the CPU path has no cold state
-        t_all, n_all = 0.0, 0
-        kind = "port"
-        for _ in range(args.steps):
-            kind, rps, dt = cpu_reference_run(w, reads, threads)
-            t_all += dt
-            n_all += len(reads)
-        value = n_all / t_all
-        sample = f"{len(reads)} read(s) per step, -t {threads} (one process, OpenMP over trellis rows)"
-        print(json.dumps({"impl": "reference", "metric": "reads decoded/s", "value": value, "unit": "reads/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-                          "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": kind,
-                                           "sample": sample},
-                          "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0,
-                                  "d2h_bytes_per_step": 0}}))
+        if rank == 0:
+            reference_arm(args, w, cfg)
         return
 
     # ------------------------------------------------------------------ our arm
     import torch
     from nanopore_dna_storage_b200.decoder import ListDecoder
+    from nanopore_dna_storage_b200.sharding import plan
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    dec = ListDecoder(w.mem_conv, w.rate, w.msg_len, w.list_size, w.max_deviation, device=local_rank,
-                      max_slots=args.slots)
-    B = args.reads_per_step or dec.slots
-    reads = synth.make_reads(w, B, start=rank * 1_000_000)
-    offsets = np.zeros(B + 1, dtype=np.uint64)
-    offsets[1:] = np.cumsum([r.post.shape[0] for r in reads])
-    flat = np.concatenate([r.post for r in reads], axis=0)
-    host_pinned = torch.empty(flat.shape, dtype=torch.float32).pin_memory()
-    host_pinned.copy_(torch.from_numpy(flat))
-    host_np = host_pinned.numpy()
-    dev_post = host_pinned.cuda(non_blocking=False)
-    work = [dec.work(int(r.post.shape[0])) for r in reads]
+    # one decoder per orientation present in the workload (C5 decodes forward and reverse-complement reads)
+    orients = [False] if w.rc_fraction <= 0 else ([True] if w.rc_fraction >= 1 else [False, True])
+    decs = {rc: ListDecoder(w.mem_conv, w.rate, w.msg_len, w.list_size, w.max_deviation, rc=rc, device=local_rank,
+                            max_slots=args.slots) for rc in orients}
+    slots = min(d.slots for d in decs.values())
+    B = args.reads_per_step or slots
+    # global read set 0 .. world*B-1, dealt by the product's length-balanced plan; rank r decodes share r
+    all_reads = synth.make_reads(w, B * world, start=0)
+    mine = plan([r.post.shape[0] for r in all_reads], world)[rank]
+    reads = [all_reads[i] for i in mine]
+    groups = {rc: [r for r in reads if r.rc == rc] for rc in orients}
+    batches = {}
+    for rc, rs in groups.items():
+        if not rs:
+            continue
+        offsets = np.zeros(len(rs) + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum([r.post.shape[0] for r in rs])
+        flat = np.concatenate([r.post for r in rs], axis=0)
+        host_pinned = torch.empty(flat.shape, dtype=torch.float32).pin_memory()
+        host_pinned.copy_(torch.from_numpy(flat))
+        batches[rc] = dict(reads=rs, offsets=offsets, host=host_pinned, host_np=host_pinned.numpy(),
+                           dev=host_pinned.cuda(non_blocking=False))
+    work = [decs[r.rc].work(int(r.post.shape[0])) for r in reads]
     step_bytes = sum(x["state_bytes"] for x in work)
     step_acs = sum(x["edge_acs"] for x in work)
     step_updates = sum(x["state_updates"] for x in work)
@@ -203,91 +297,133 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def run_device():
-        return dec.decode_packed(None, offsets, device_ptr=dev_post.data_ptr())
-
-    def run_host():
-        return dec.decode_packed(host_np, offsets)
+    def run(device_resident: bool, acc: dict):
+        outs = {}
+        for rc, b in batches.items():
+            if device_resident:
+                outs[rc] = decs[rc].decode_packed(None, b["offsets"], device_ptr=b["dev"].data_ptr())
+            else:
+                outs[rc] = decs[rc].decode_packed(b["host_np"], b["offsets"])
+            tm = decs[rc].timing()
+            for k in ("kernel_ms", "total_ms", "launches", "step_launches", "exact_fallbacks", "h2d_bytes", "d2h_bytes",
+                      "chain_inserts"):
+                acc[k] = acc.get(k, 0) + tm[k]
+            acc["chain_keys_max"] = max(acc.get("chain_keys_max", 0), tm["chain_keys_max"])
+            acc["chain_table_slots"] = tm["chain_table_slots"]
+        return outs
 
     for _ in range(args.warmup):
-        out_dev = run_device()
+        run(True, {})
     # ---- timed: device-resident inputs ----
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
-    kernel_ms = total_ms = 0.0
-    launches = step_launches = fallbacks = 0
+    dev_acc = {}
     for _ in range(args.steps):
-        out_dev = run_device()
-        tm = dec.timing()
-        kernel_ms += tm["kernel_ms"]; total_ms += tm["total_ms"]
-        launches += tm["launches"]; step_launches += tm["step_launches"]; fallbacks += tm["exact_fallbacks"]
+        out_dev = run(True, dev_acc)
     barrier()
     wall = time.perf_counter() - t0
     # ---- timed: host buffers through the C ABI (e2e) ----
     for _ in range(min(args.warmup, 1)):
-        run_host()
+        run(False, {})
     barrier()
     t1 = time.perf_counter()
-    h2d = d2h = 0
+    host_acc = {}
     for _ in range(args.steps):
-        out_host = run_host()
-        tm = dec.timing()
-        h2d += tm["h2d_bytes"]; d2h += tm["d2h_bytes"]
+        out_host = run(False, host_acc)
     barrier()
     wall_e2e = time.perf_counter() - t1
     clocks = sampler.stop() if rank == 0 else None
-    assert np.array_equal(out_dev[0], out_host[0]) and np.array_equal(out_dev[2], out_host[2])
 
-    times = torch.tensor([wall, wall_e2e, kernel_ms, total_ms], dtype=torch.float64, device="cuda")
+    # ---- outside the timed region: parity of what was just decoded ----
+    lists = {}
+    for rc, b in batches.items():
+        assert np.array_equal(out_dev[rc][0], out_host[rc][0]) and np.array_equal(out_dev[rc][2], out_host[rc][2])
+        bits, _, counts, _ = out_dev[rc]
+        for k, r in enumerate(b["reads"]):
+            lists[r.index] = lines_of(bits[k, :counts[k]])
+    gold = golden_lists(w)
+    fixture_checked = 0
+    for r in reads:
+        if r.index in gold:
+            assert lists[r.index] == gold[r.index][0], f"GPU list of read {r.index} differs from the reference fixture"
+            fixture_checked += 1
+    ncorrect = sum(1 for r in reads if lists[r.index] and lists[r.index][0] == "".join(map(str, r.msg.tolist())))
+
+    times = torch.tensor([wall, wall_e2e, dev_acc["kernel_ms"], dev_acc["total_ms"]], dtype=torch.float64, device="cuda")
+    counts_t = torch.tensor([len(reads), fixture_checked, ncorrect], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts_t, op=dist.ReduceOp.SUM)
     wall, wall_e2e, kernel_ms, total_ms = [float(x) for x in times.tolist()]
+    n_reads_all, fixture_all, ncorrect_all = [int(x) for x in counts_t.tolist()]
 
     if rank == 0:
-        n_total = B * args.steps * world
+        n_total = n_reads_all * args.steps
         value = n_total / wall
-        peak, peak_src = measured_peak_hbm()
+        peak, sm_max_mhz, peak_src = measured_peaks()
         achieved = step_bytes * args.steps / (kernel_ms * 1e-3) / 1e9  # per GPU: bytes of one rank / its kernel time
-        tr = ncu_traffic()
-        ncorrect = sum(1 for i, r in enumerate(reads)
-                       if out_dev[2][i] > 0 and np.array_equal(out_dev[0][i, 0], r.msg))
+        tr = committed_json("traffic.json")
+        step_launches = int(dev_acc["step_launches"])
+        cand_acs_per_s = step_acs * w.list_size * args.steps / (kernel_ms * 1e-3)  # one GPU, kernel time
+        alu_peak = ISSUE_PEAK_THREAD_INSTR * sm_max_mhz * 1e6 / 2.0  # 2 thread-instructions per candidate-ACS
         line = {
             "metric": "reads decoded/s", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(cfg, reads_per_step_per_gpu=B, slots=dec.slots,
-                                                l2_note="state ping-pong per step >> 126 MB L2 (no reuse across steps)"),
+            "data": "synthetic", "config": cfg,
+            "batch": {"reads_per_step_per_gpu": B, "slots": slots, "orientations": len(batches),
+                      "l2_note": "state ping-pong per step (8 GB at 64 reads) >> 126 MB L2: no flush needed between steps",
+                      "sharding": "nanopore_dna_storage_b200.sharding.plan over the global read set"},
             "acs_updates_per_s": step_acs * args.steps * world / wall,
             "state_updates_per_s": step_updates * args.steps * world / wall,
             "device_ms_per_step": total_ms / args.steps, "kernel_ms_per_step": kernel_ms / args.steps,
-            "gpu_launches": int(launches), "step_kernel_launches": int(step_launches),
-            "exact_fallbacks": int(fallbacks), "top1_correct_frac": ncorrect / B,
-            "e2e": {"value": n_total / wall_e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps,
-                    "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": int(dev_acc["launches"] + host_acc["launches"]), "step_kernel_launches": step_launches,
+            "exact_fallbacks": int(dev_acc["exact_fallbacks"]), "top1_correct_frac": ncorrect_all / n_reads_all,
+            "chain_tables": {"keys_per_read_max": int(dev_acc["chain_keys_max"]),
+                             "keys_per_read_mean": dev_acc["chain_inserts"] / max(1, len(reads) * args.steps),
+                             "slots_per_read": int(dev_acc["chain_table_slots"])},
+            "parity": {"reads_checked_against_reference_fixtures": fixture_all,
+                       "fixtures": "tests/golden/reference_lists_r2.json (unmodified reference, same reads)"},
+            "e2e": {"value": n_total / wall_e2e, "unit": "reads/s",
+                    "h2d_bytes_per_step": int(host_acc["h2d_bytes"]) // args.steps,
+                    "d2h_bytes_per_step": int(host_acc["d2h_bytes"]) // args.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
-                         "kernel": "lva_step_fast<LP,NWD> (all step launches)",
+                         "kernel": "lva_step_fast<LP> (every trellis step launch)",
                          "algorithmic_bytes_per_step": step_bytes,
                          "avg_launch_us": 1e3 * kernel_ms / max(step_launches, 1),
                          "traffic": tr.get("dram_bytes_per_launch") if tr else None,
-                         "traffic_note": (f"ncu capture of {tr['kernel']}: {tr['dram_bytes_per_launch']} B DRAM vs "
-                                          f"{tr['algorithmic_bytes_same_launch']} B algorithmic for that launch") if tr else None},
+                         "traffic_note": tr.get("note") if tr else None,
+                         "alu": {"cand_acs_per_s": cand_acs_per_s, "peak": alu_peak, "frac": cand_acs_per_s / alu_peak,
+                                 "note": "SURVEY.md 8(d) issue-slot ceiling: 2 thread-instructions per candidate-ACS"}},
             "clocks": clocks,
         }
-        pipes = ncu_pipes()
+        pipes = committed_json("pipes.json")
         if pipes and args.workload == "C2":
-            line["roofline"]["issue"] = {k: pipes[k] for k in ("issue_active_pct", "alu_pipe_pct", "fma_pipe_pct",
-                                                               "lsu_pipe_pct", "source") if k in pipes}
+            line["roofline"]["issue_committed_capture"] = pipes
         if world == 1 and not args.no_cpu_baseline:
-            cpu_reads = synth.make_reads(w, max(1, args.cpu_reads), start=10_000_000)
-            kind, rps, dt = cpu_reference_run(w, cpu_reads, threads)
-            line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": threads, "kind": kind,
-                                    "sample": f"{len(cpu_reads)} read(s) of the same workload, one process -t {threads}, {dt:.1f} s"}
+            # bounded live CPU sample: reads of THIS batch through the unmodified reference (latency mode keeps
+            # it to ~15 s per read), lists compared byte for byte with what the GPU just produced
+            from oracle import binding as ob
+            sample_reads = reads[:max(1, args.cpu_reads)]
+            with tempfile.TemporaryDirectory() as tmp:
+                if ob.have_ref():
+                    dt, out = ref_cli_decode_many(w, sample_reads, 1, cores, tmp)
+                    kind = "reference"
+                else:
+                    dt, out = oracle_port_decode_many(w, sample_reads, cores)
+                    kind = "port"
+            for r in sample_reads:
+                assert out[r.index] == lists[r.index], f"GPU list of read {r.index} differs from the CPU {kind}"
+            line["cpu_baseline"] = {"value": len(sample_reads) / dt, "unit": "reads/s", "cores": cores, "kind": kind,
+                                    "sample": f"reads {[r.index for r in sample_reads]} of the GPU batch, one process -t {cores}, "
+                                              f"{dt:.1f} s; lists byte-equal to the GPU output"}
         print(json.dumps(line))
-    dec.close()
+    for d in decs.values():
+        d.close()
     if world > 1:
         dist.destroy_process_group()
 
