@@ -335,11 +335,14 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   }
   h->nid_parity_words = (unsigned long long)h->nid_ring * k.nconv * 8ull * h->LP;
   {
-    // interning table: distinct (chain id, chunk) pairs per read.  Sized generously; a probe chain
-    // that runs away raises a flag and the call is repeated with a larger table.
-    uint64_t want = (uint64_t)k.nconv * 4096ull;
+    // interning table: distinct (chain id, chunk) pairs per read.  Measured: up to 4.2 M keys per
+    // C2 read (m=11, L=8, six chunks; hard reads need the most), 7.6 M at L=16, 1.2 M at m=14 with
+    // three chunks -- the count follows the list size and the noise of the read, not the state count.
+    // Default 8 M slots per 8 list slots; a call that fills a table beyond ~45 % grows them for the
+    // next call, a probe chain that runs away raises a flag and the call is repeated with larger tables.
+    uint64_t want = (1ull << 23) * std::max<uint64_t>(1, (h->LP + 7) / 8);
     if (const char *e2 = getenv("LVA_TAB_LOG2")) want = 1ull << std::min(28, std::max(10, atoi(e2)));
-    want = std::min<uint64_t>(std::max<uint64_t>(want, 1ull << 16), 1ull << 26);
+    want = std::min<uint64_t>(std::max<uint64_t>(want, 1ull << 16), 1ull << 27);
     h->tab_slots = next_pow2((uint32_t)want);
     if (k.nchunks == 0) h->tab_slots = 1024;  // short messages: nothing is ever interned
   }
@@ -663,6 +666,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *start
         const uint32_t st = band[rd[s].band_off + t], en = band_end(st, k.nrows, h->max_dev);
         span = std::max(span, en - st);
         a.band_a[s] = (uint16_t)st;
+        a.band_slot[s] = (uint16_t)(st % h->window);
         a.post_blk[s] = (uint32_t)(rd[s].post_block + t);
         clr.row[s] = 0xFFFFu;
         if (!h->survivor && t > 0 && en > 0) {
@@ -853,7 +857,13 @@ static int decode_entry(lva_handle *h, const float *post, bool post_on_device, c
     CK(cudaMemcpy(cnt, h->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost));
     h->timing.exact_fallbacks = cnt[0];
     h->timing.chain_table_slots = h->tab_slots;
-    if (cnt[1] == 0) break;
+    if (cnt[1] == 0) {
+      // proactive growth for the next call: linear probing degrades quickly above half full
+      if (!h->survivor && h->timing.chain_keys_max * 20ull > (unsigned long long)h->tab_slots * 9ull && h->tab_slots < (1u << 27) &&
+          h->d_tab.ensure((size_t)h->n_slots * h->tab_slots * 2 * 8))
+        h->tab_slots *= 2;
+      break;
+    }
     // a chain table filled up: every result of this call is suspect.  Grow the tables and decode again.
     if (attempt == 3 || h->tab_slots >= (1u << 27)) { h->err = "chain table overflow"; return LVA_ERR_OOM; }
     h->tab_slots *= 4;

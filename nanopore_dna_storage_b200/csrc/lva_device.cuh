@@ -85,10 +85,10 @@ struct StepArgs {
   uint32_t tab_mask;              // tab_slots - 1
   uint32_t t, dev2, code_slot;
   uint32_t row_lo, row_hi;        // rows this launch is responsible for
-  uint32_t dbg;                   // developer ablations (LVA_DBG), 0 in production
+  uint32_t dbg;                   // developer switches (LVA_DBG), 0 in production: bit 1 data movement only, bit 4 no stores, bits 8.. L2 prefetch distance in CTAs
   uint32_t post_blk[kMaxSlots];   // per active slot: index of the posterior block of this step
   uint16_t band_a[kMaxSlots];     // per active slot: first in-band row of this step (VCC:677-678)
-  uint16_t fresh[kMaxSlots];      // per active slot: rows >= fresh enter the band at this step (their window slot holds a recycled row: own list = -inf)
+  uint16_t band_slot[kMaxSlots];  // per active slot: band_a % window (the window slot of the first in-band row)
 };
 
 struct FinalArgs {

@@ -159,9 +159,36 @@ __device__ __forceinline__ void select_head(const float (&h)[NL], float &best, i
 // the loop ends.
 // Returns the number of accepted entries, or -1 on a tie (caller falls back to exact_merge and
 // overwrites whatever was stored).
+// Rows without any history bit yet (the first rows of the trellis): every candidate of a state carries
+// the same (empty) message, so the new list is the best head alone (VCC:743-800 drops all the others as
+// duplicates).  Returns 0 / 1, or -1 when another head ties with the best (heap order decides).
 template <int LP, int NL>
-__device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL> &V, int L, bool nohist,
-                                           AcceptLog<LP> &log, uint32_t dbg = 0) {
+__device__ __forceinline__ int merge_first_only(uint32_t *dst, const ListView<LP, NL> &V, AcceptLog<LP> &log) {
+  constexpr uint32_t GP = 64u * LP;
+  float h[NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++) h[i] = V.score(i, 0);
+  float best;
+  int i;
+  select_head<NL>(h, best, i);
+  log.clear();
+  if (best == neg_inf()) return 0;
+  bool tie = false;
+#pragma unroll
+  for (int i2 = 0; i2 < NL; i2++) tie = tie || (i2 != i && h[i2] == best);
+  uint32_t cid, cpt;
+  V.identity(i, 0, cid, cpt);
+  __stcs(dst, __float_as_uint(best));
+  __stcs(dst + GP, cid);
+  __stcs(dst + 2 * GP, cpt);
+  log.push(AcceptLog<LP>::signature(cid ^ cpt), (uint32_t)(i << 4));
+  return tie ? -1 : 1;
+}
+
+// FULL: the list size equals the slot count (L == LP), the usual case: one constant less in the loop.
+template <int LP, int NL, bool FULL>
+__device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL> &V, int L_rt, AcceptLog<LP> &log) {
+  const int L = FULL ? LP : L_rt;
   constexpr uint32_t GP = 64u * LP;  // words between the planes of a list in HBM
   const float NEG = neg_inf();
   float h[NL];
@@ -195,20 +222,14 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL>
     select_head<NL>(h, nbest, ni);
     // ---- chain A continued: de-duplicate, accept ----
     tie = tie || (best == last_acc && i != last_i);
-    bool dup;
-    if (nohist) {
-      dup = l > 0;
-    } else {
-      uint32_t m = log.match(csig);
-      dup = false;
-      if (dbg & 1u) { dup = m != 0; m = 0; }  // ablation: a signature match counts as a duplicate (WRONG results)
-      while (m != 0 && !dup) {
-        const uint32_t d = log.desc_at(__ffs(m) - 1);
-        m &= m - 1u;
-        uint32_t aid, apt;
-        V.identity((int)(d >> 4), (int)(d & 15u), aid, apt);
-        dup = aid == cid && apt == cpt;
-      }
+    uint32_t m = log.match(csig);
+    bool dup = false;
+    while (m != 0 && !dup) {
+      const uint32_t d = log.desc_at(__ffs(m) - 1);
+      m &= m - 1u;
+      uint32_t aid, apt;
+      V.identity((int)(d >> 4), (int)(d & 15u), aid, apt);
+      dup = aid == cid && apt == cpt;
     }
     if (!dup) {
       last_acc = best;
@@ -220,7 +241,7 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL>
       dst += 8;
       log.push(csig, (uint32_t)((i << 4) | j));
       l++;
-      if (l == L || nohist) break;  // nohist: every further candidate carries the same (empty) history
+      if (l == L) break;
     }
     if (nbest == NEG) break;
     best = nbest;
@@ -254,8 +275,12 @@ __device__ __forceinline__ void publish_ids(const ListView<LP, NL> &V, const Acc
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 template <int LP>
-__global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, const __grid_constant__ CUtensorMap src_map,
+__global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs A, const __grid_constant__ CUtensorMap src_map,
                                                               const __grid_constant__ CUtensorMap own_map,
                                                               const __grid_constant__ CUtensorMap nid_map) {
   constexpr int TG = 32;
@@ -266,8 +291,7 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
   const uint32_t a = A.band_a[z];
   uint32_t bend = a + A.dev2;
   if (bend > K.nrows) bend = K.nrows;
-  if (bend > A.row_hi) bend = A.row_hi;
-  const uint32_t p = (a > A.row_lo ? a : A.row_lo) + blockIdx.y;
+  const uint32_t p = a + blockIdx.y;
   if (p >= bend) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tile = blockIdx.x;
@@ -276,6 +300,10 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
     return;
   }
   const RowDev R = K.row[p];
+  // window slots of rows p and p-1 (p % window without a division: the band never spans more than the window)
+  uint32_t wp = A.band_slot[z] + blockIdx.y;
+  if (wp >= K.window) wp -= K.window;
+  const uint32_t wp1 = wp == 0 ? K.window - 1 : wp - 1;
   // Rows entered by a one-bit step (puncturing block 0) can produce only two of the four bases
   // per conv state: the other two flip states and their flop states have no predecessor, are
   // never reached and keep their -inf.  On such rows warps 0-1 handle the 64 live flip targets
@@ -306,39 +334,22 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
   }
   if (!__syncthreads_or(valid)) return;
 
-  const int L = (int)K.L;
   const uint32_t ppr = K.nconv >> 3;  // pieces per row
+  const uint32_t prv_row0 = (z * 2u + (A.t & 1u)) * K.window, cur_row0 = (z * 2u + ((A.t + 1u) & 1u)) * K.window;
   // ---- stage ----
   if (tid == 0) {
     const uint32_t src_planes = R.post_boundary ? 1u : 3u;
     const uint32_t plane_bytes = 8u * LP * TG * 4u, warp_bytes = 3u * LP * TG * 4u;
     mbar_expect_tx(bar, 160u + (src_planes + (R.post_boundary ? 1u : 0u)) * plane_bytes + 8u * warp_bytes);
     bulk_g2s(post, A.post + (unsigned long long)A.post_blk[z] * 40, 160u, bar);
-    const uint32_t prv_row = ((z * 2u + (A.t & 1u)) * K.window);
-    const int src_piece = (int)((prv_row + (p - 1) % K.window) * ppr + tile * 4u);
-    if (A.dbg & 4u) {  // ablation: the tile as ONE contiguous bulk copy (wrong shared-memory layout)
-      bulk_g2s(src, A.state + row_base(A, K, z, A.t & 1u, p - 1) + (unsigned long long)tile * 4u * A.piece_words,
-               src_planes * plane_bytes, bar);
-    } else {
-      for (uint32_t pl = 0; pl < src_planes; pl++)
-        tensor3d_g2s(src + pl * 8 * LP * TG, &src_map, 0, src_piece, (int)(pl * 8 * LP), bar);
-    }
+    const int src_piece = (int)((prv_row0 + wp1) * ppr + tile * 4u);
+    for (uint32_t pl = 0; pl < src_planes; pl++)
+      tensor3d_g2s(src + pl * 8 * LP * TG, &src_map, 0, src_piece, (int)(pl * 8 * LP), bar);
     if (R.post_boundary)  // the chain ids of a completed chunk come from the source row's nid plane
       tensor3d_g2s(src + 8 * LP * TG, &nid_map, 0,
                    (int)(((z * 2u + (A.t & 1u)) * K.nid_ring + R.src_nid_slot) * ppr + tile * 4u), 0, bar);
-    const int own_piece0 = (int)((prv_row + p % K.window) * ppr);
-    if (A.dbg & 8u) {  // ablation: own lists as contiguous bulk copies (wrong shared-memory layout)
-      const uint32_t *rowp = A.state + row_base(A, K, z, A.t & 1u, p);
-      if (!one_bit) {
-        for (uint32_t w = 0; w < 8; w++)
-          bulk_g2s(own + w * 3 * LP * TG, rowp + (unsigned long long)(((w & 3u) << (K.mem - 5)) + tile) * A.piece_words + (w >> 2) * 3u * LP * TG,
-                   warp_bytes, bar);
-      } else {
-        for (uint32_t w = 0; w < 4; w++)
-          bulk_g2s(own + w * 6 * LP * TG, rowp + (unsigned long long)(((w & 1u) << (K.mem - 4)) + tile * 2u) * A.piece_words + (w >> 1) * 6u * LP * TG,
-                   2u * warp_bytes, bar);
-      }
-    } else if (!one_bit) {
+    const int own_piece0 = (int)((prv_row0 + wp) * ppr);
+    if (!one_bit) {
       for (uint32_t w = 0; w < 8; w++)
         tensor5d_g2s(own + w * 3 * LP * TG, &own_map, 0, (int)(4u * (w >> 2)), 0, 0,
                      own_piece0 + (int)(((w & 3u) << (K.mem - 5)) + tile), bar);
@@ -347,6 +358,30 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
         for (uint32_t h = 0; h < 2; h++)
           tensor5d_g2s(own + (w * 2 + h) * 3 * LP * TG, &own_map, 0, (int)(4u * (w >> 1)), 0, 0,
                        own_piece0 + (int)(((w & 1u) << (K.mem - 4)) + tile * 2u + h), bar);
+    }
+    if (A.dbg >> 8) {
+      // developer switch: pull the lists of the CTA `dist` places later in launch order into L2 now
+      const uint32_t dist = A.dbg >> 8;
+      uint32_t n = (z * gridDim.y + blockIdx.y) * gridDim.x + tile + dist;
+      const uint32_t t2 = n % gridDim.x, y2 = (n / gridDim.x) % gridDim.y, z2 = n / (gridDim.x * gridDim.y);
+      if (z2 < gridDim.z) {
+        const uint32_t a2 = A.band_a[z2], p2 = a2 + y2;
+        uint32_t b2 = a2 + A.dev2;
+        if (b2 > K.nrows) b2 = K.nrows;
+        if (p2 > 0 && p2 < b2) {
+          uint32_t w2 = A.band_slot[z2] + y2;
+          if (w2 >= K.window) w2 -= K.window;
+          const uint32_t w21 = w2 == 0 ? K.window - 1 : w2 - 1;
+          const uint32_t *base2 = A.state + ((unsigned long long)z2 * 2 + (A.t & 1u)) * A.parity_words;
+          prefetch_l2(base2 + (unsigned long long)w21 * A.row_words + (unsigned long long)t2 * 4u * A.piece_words, 4u * A.piece_words * 4u);
+          const uint32_t *row2 = base2 + (unsigned long long)w2 * A.row_words;
+          if (K.row[p2].shift != 1) {
+            for (uint32_t r = 0; r < 4; r++) prefetch_l2(row2 + (unsigned long long)((r << (K.mem - 5)) + t2) * A.piece_words, A.piece_words * 4u);
+          } else {
+            for (uint32_t r = 0; r < 2; r++) prefetch_l2(row2 + (unsigned long long)((r << (K.mem - 4)) + t2 * 2u) * A.piece_words, 2u * A.piece_words * 4u);
+          }
+        }
+      }
     }
   }
   // ---- the rest of the geometry, while the copies fly: my crf state and predecessor column ----
@@ -366,15 +401,15 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
     src_g = (int)((idx << 1) | xy);
     pos = (warp * 2 + (int)(idx >> 3)) * 3 * LP * TG + (int)(b * 8u + (idx & 7u));
   }
-  const unsigned long long own_off = (unsigned long long)(c >> 3) * A.piece_words + (unsigned long long)s * LP * 8 + (c & 7u);
-  uint32_t *dst = A.state + row_base(A, K, z, (A.t + 1u) & 1u, p) + own_off;
+  const uint32_t own_off = (c >> 3) * A.piece_words + (uint32_t)s * LP * 8 + (c & 7u);  // inside a row (< 2^32 words)
+  uint32_t *dst = A.state + (unsigned long long)(cur_row0 + wp) * A.row_words + own_off;
   const uint32_t appv = appended_bits(xy, R.shift, R.app) << R.app_pos;
   const uint32_t keep = R.post_boundary ? 0u : 0xffffffffu;
   mbar_wait(bar, 0);
   if (!valid) return;
 
   uint32_t *mine = own + pos;
-  if (A.dbg & 2u) {  // ablation: data movement only -- the own list is copied to the new list (WRONG results)
+  if (A.dbg & 2u) {  // developer switch: data movement only -- the own list is copied to the new list (WRONG results)
     if (A.dbg & 16u) { if (mine[0] == 0x12345678u) dst[0] = src[src_g]; return; }  // ... and no stores
 #pragma unroll
     for (int l = 0; l < LP; l++) {
@@ -384,6 +419,7 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
     }
     return;
   }
+  const int L = (int)K.L;
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
   const uint32_t *srcg = src + src_g;
@@ -401,12 +437,16 @@ __global__ void __launch_bounds__(kFastThreads) lva_step_fast(const StepArgs A, 
   if (role == 0) {
     ListView<LP, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    n_acc = merge_lists<LP, 8>(dst, V, L, R.nohist != 0, log, A.dbg);
+    if (R.nohist) n_acc = merge_first_only<LP, 8>(dst, V, log);
+    else if (L == LP) n_acc = merge_lists<LP, 8, true>(dst, V, L, log);
+    else n_acc = merge_lists<LP, 8, false>(dst, V, L, log);
     if (R.boundary && n_acc > 0) publish_ids<LP, 8>(V, log, n_acc, nidw, nid_own, tab, A, z);
   } else {
     ListView<LP, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    n_acc = merge_lists<LP, 2>(dst, V, L, R.nohist != 0, log, A.dbg);
+    if (R.nohist) n_acc = merge_first_only<LP, 2>(dst, V, log);
+    else if (L == LP) n_acc = merge_lists<LP, 2, true>(dst, V, L, log);
+    else n_acc = merge_lists<LP, 2, false>(dst, V, L, log);
     if (R.boundary && n_acc > 0) publish_ids<LP, 2>(V, log, n_acc, nidw, nid_own, tab, A, z);
   }
   if (n_acc < 0) {  // metrics tie where libstdc++'s heap order could show: redo this state exactly

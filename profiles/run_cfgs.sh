@@ -1,7 +1,10 @@
 #!/bin/bash
-# scratch: bench lines of the other configs (not part of the product)
-mkdir -p gpurun_out
-python bench.py --steps 1 --warmup 1 --no-cpu-baseline --slots 128 > gpurun_out/c2_s128.log 2>&1
-for wl in "$@"; do python bench.py --workload $wl --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/cfg_$wl.log 2>&1; done
-tail -c 600 gpurun_out/c2_s128.log | cut -c1-120
-for wl in "$@"; do echo == $wl; tail -c 1500 gpurun_out/cfg_$wl.log | cut -c1-400; done
+# the other BASELINE.json configs on one B200 (bench.py, no live CPU sample): one JSON line each
+for wl in C1 C3 C4r2 C4r7 C5; do
+  echo "== $wl"
+  timeout 600 python bench.py --workload $wl --steps 2 --warmup 1 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+print(json.dumps({k:d[k] for k in ('value','ms_per_step','batch','kernel_ms_per_step','exact_fallbacks','top1_correct_frac','chain_tables','parity')}))
+print(json.dumps({'e2e':d['e2e'],'roofline_frac':d['roofline']['frac'],'achieved':d['roofline']['achieved'],'alu':d['roofline']['alu']['frac']}))"
+done
