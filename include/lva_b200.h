@@ -61,6 +61,12 @@ typedef struct lva_params {
 } lva_params;
 
 #define LVA_FLAG_EXACT_ONLY 1u /* run every state through the exact heap-order merge (validation mode) */
+/* Band start of VCC:677-679 with the product t/nblk*nstate_pos rounded BEFORE max_deviation is
+ * subtracted.  Default (flag clear) is the fused multiply-subtract g++ -O3 -march=native emits for the
+ * reference on FMA hardware (install.sh:10); set this to match a reference built with
+ * -ffp-contract=off, with clang, or for a CPU without FMA.  The two differ by one trellis row on a few
+ * steps of some read lengths (e.g. C2 reads whose length is a multiple of 29). */
+#define LVA_FLAG_UNFUSED_BAND 2u
 
 typedef struct lva_handle lva_handle;
 
@@ -131,9 +137,12 @@ typedef struct lva_code_tables {
 int lva_get_code_tables(uint32_t mem_conv, uint32_t rate, uint32_t msg_len, int32_t rc,
                         const char *sync_marker, uint32_t sync_period, lva_code_tables *out);
 
-/* band of VCC:677-679 for step t of a read of nblk blocks: [*start, *end) */
+/* band of VCC:677-679 for step t of a read of nblk blocks: [*start, *end) (fused form; lva_band_ex
+ * takes LVA_FLAG_UNFUSED_BAND in flags) */
 void lva_band(uint32_t t, uint32_t nblk, uint32_t nstate_pos, uint32_t max_deviation,
               uint32_t *start, uint32_t *end);
+void lva_band_ex(uint32_t t, uint32_t nblk, uint32_t nstate_pos, uint32_t max_deviation, uint32_t flags,
+                 uint32_t *start, uint32_t *end);
 
 /* Geometry a caller may want (nstate_pos of VCC:74; bases per oligo = nstate_pos - 1). */
 uint32_t lva_nstate_pos(const lva_handle *h);

@@ -13,9 +13,10 @@ CLI_PATH = os.path.join(HERE, "_build", "viterbi_nanopore.out")
 
 LVA_DEFAULT_DEVIATION = 0xFFFFFFFF
 LVA_FLAG_EXACT_ONLY = 1
+LVA_FLAG_UNFUSED_BAND = 2
 
 EXPORTS = ["lva_create", "lva_destroy", "lva_last_error", "lva_decode_batch", "lva_decode_batch_device", "lva_decode_batch_crc", "lva_decode_ranges",
-           "lva_trim_batch", "lva_posteriors_batch", "lva_posteriors_batch_device", "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_device_count", "lva_version"]
+           "lva_trim_batch", "lva_posteriors_batch", "lva_posteriors_batch_device", "lva_encode", "lva_check_params", "lva_get_code_tables", "lva_band", "lva_band_ex", "lva_nstate_pos", "lva_slots", "lva_count_work", "lva_get_timing", "lva_device_count", "lva_version"]
 
 
 class LvaParams(C.Structure):
@@ -99,6 +100,8 @@ def lib() -> C.CDLL:
                                       C.POINTER(LvaCodeTables)]
     L.lva_band.restype = None
     L.lva_band.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)] * 2
+    L.lva_band_ex.restype = None
+    L.lva_band_ex.argtypes = [C.c_uint32] * 5 + [C.POINTER(C.c_uint32)] * 2
     L.lva_check_params.restype = C.c_int
     L.lva_check_params.argtypes = [C.c_uint32] * 3
     L.lva_version.restype = C.c_char_p

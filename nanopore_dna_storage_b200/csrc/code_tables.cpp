@@ -146,9 +146,15 @@ int build_code_spec(CodeSpec &k, uint32_t mem, uint32_t rate, uint32_t msg_len, 
   return kCodeOk;
 }
 
-uint32_t band_start(uint32_t t, uint32_t nblk, uint32_t nrows, uint32_t max_deviation) {
+uint32_t band_start(uint32_t t, uint32_t nblk, uint32_t nrows, uint32_t max_deviation, bool fused) {
   const double frac = (double)t / (double)nblk;
-  const double v = std::fma(frac, (double)nrows, -(double)max_deviation);
+  double v;
+  if (fused) {
+    v = std::fma(frac, (double)nrows, -(double)max_deviation);
+  } else {
+    volatile double prod = frac * (double)nrows;  // rounded product (volatile: no contraction by this build either)
+    v = prod - (double)max_deviation;
+  }
   const int64_t a = (int64_t)v;
   return a < 0 ? 0u : (uint32_t)a;
 }

@@ -63,9 +63,12 @@ struct CodeSpec {
 int build_code_spec(CodeSpec &k, uint32_t mem, uint32_t rate, uint32_t msg_len, bool rc,
                     const std::string &marker, uint32_t period);
 
-// band start of time step t (VCC:677-679; fused multiply-subtract as the -O3 -march=native
-// reference build evaluates it on FMA hardware)
-uint32_t band_start(uint32_t t, uint32_t nblk, uint32_t nrows, uint32_t max_deviation);
+// band start of time step t (VCC:677-679).  fused = true: t/nblk*nstate_pos - max_deviation evaluated
+// as ONE fused multiply-subtract, which is what g++ -O3 emits for the reference on FMA hardware
+// (install.sh:10 builds with -march=native); fused = false: product rounded first (a reference
+// built with -ffp-contract=off, by clang, or for a CPU without FMA).  The two differ by one row for
+// some (t, nblk), e.g. whenever nblk shares a factor with nstate_pos.
+uint32_t band_start(uint32_t t, uint32_t nblk, uint32_t nrows, uint32_t max_deviation, bool fused = true);
 inline uint32_t band_end(uint32_t a, uint32_t nrows, uint32_t max_deviation) {
   uint32_t e = a + 2u * max_deviation;  // uint32 arithmetic as in the reference
   return e < nrows ? e : nrows;

@@ -53,6 +53,16 @@ struct DevBuf {
     cap = n;
     return true;
   }
+  // like ensure(), but the old allocation survives a failed attempt
+  bool try_grow(size_t n) {
+    if (n <= cap) return true;
+    void *q = nullptr;
+    if (cudaMalloc(&q, n) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (p) cudaFree(p);
+    p = q;
+    cap = n;
+    return true;
+  }
   ~DevBuf() { if (p) cudaFree(p); }
 };
 
@@ -86,6 +96,7 @@ struct lva_handle {
   size_t gen_smem = 0;
   bool use_fast = false;
   bool all_one_bit = false;
+  bool fused_band = true;    // VCC:677-679 as a fused multiply-subtract (LVA_FLAG_UNFUSED_BAND clears it)
 };
 
 namespace {
@@ -292,6 +303,7 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   // List size 1 needs no message identity at all (VCC:715-742 has no de-duplication): keep metrics
   // only, record one 4-bit decision per state and step, rebuild the message by traceback.
   h->survivor = h->L == 1 && !(params->flags & LVA_FLAG_EXACT_ONLY);
+  h->fused_band = !(params->flags & LVA_FLAG_UNFUSED_BAND);
   h->all_one_bit = true;
   for (uint32_t r = 1; r < k.nrows; r++) h->all_one_bit = h->all_one_bit && k.shift[r] == 1;
 
@@ -474,7 +486,7 @@ int lva_count_work(const lva_handle *h, uint32_t T, lva_work *out) {
   const CodeSpec &k = h->code;
   out->state_updates = out->edge_acs = out->state_bytes = 0;
   for (uint32_t t = 0; t < T; t++) {
-    const uint32_t a = band_start(t, T, k.nrows, h->max_dev), b = band_end(a, k.nrows, h->max_dev);
+    const uint32_t a = band_start(t, T, k.nrows, h->max_dev, h->fused_band), b = band_end(a, k.nrows, h->max_dev);
     for (uint32_t p = a; p < b; p++) {
       const double nst = std::ldexp(8.0, (int)k.mem - __builtin_popcount(k.vmask[p]));
       out->state_updates += nst;
@@ -523,11 +535,15 @@ int lva_get_code_tables(uint32_t mem_conv, uint32_t rate, uint32_t msg_len, int3
   return LVA_OK;
 }
 
-void lva_band(uint32_t t, uint32_t nblk, uint32_t nstate_pos, uint32_t max_deviation, uint32_t *start,
-              uint32_t *end) {
-  const uint32_t a = band_start(t, nblk, nstate_pos, max_deviation);
+void lva_band_ex(uint32_t t, uint32_t nblk, uint32_t nstate_pos, uint32_t max_deviation, uint32_t flags, uint32_t *start,
+                 uint32_t *end) {
+  const uint32_t a = band_start(t, nblk, nstate_pos, max_deviation, !(flags & LVA_FLAG_UNFUSED_BAND));
   if (start) *start = a;
   if (end) *end = band_end(a, nstate_pos, max_deviation);
+}
+void lva_band(uint32_t t, uint32_t nblk, uint32_t nstate_pos, uint32_t max_deviation, uint32_t *start,
+              uint32_t *end) {
+  lva_band_ex(t, nblk, nstate_pos, max_deviation, 0, start, end);
 }
 
 int lva_encode(uint32_t mem_conv, uint32_t rate, const uint8_t *msg, uint32_t msg_len, uint8_t *out_bits,
@@ -602,7 +618,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *start
       rd[s].post_block = starts[i];
       rd[s].T = T;
       rd[s].band_off = (uint32_t)bo;
-      for (uint32_t t = 0; t < T; t++) band[bo + t] = (uint16_t)band_start(t, T, k.nrows, h->max_dev);
+      for (uint32_t t = 0; t < T; t++) band[bo + t] = (uint16_t)band_start(t, T, k.nrows, h->max_dev, h->fused_band);
       bo += T;
     }
     CK(cudaMemcpyAsync(h->d_reads.p, rd, sizeof(ReadDev) * ns, cudaMemcpyHostToDevice, h->stream));
@@ -848,7 +864,13 @@ static int decode_entry(lva_handle *h, const float *post, bool post_on_device, c
     h->timing.h2d_bytes += bytes;
   }
   CK(cudaEventRecord(h->ev[1], h->stream));
+  const lva_timing before = h->timing;
   for (int attempt = 0;; attempt++) {
+    {  // a repeated attempt starts its accounting afresh
+      const uint64_t regrows = h->timing.table_regrows;
+      h->timing = before;
+      h->timing.table_regrows = regrows;
+    }
     CK(cudaMemsetAsync(h->d_counters.p, 0, kCounterBytes, h->stream));
     h->timing.chain_keys_max = 0;
     int st = decode_core(h, d_post, starts, ends, n_reads, crc, out_bits, out_scores, out_counts, out_status);
@@ -860,15 +882,15 @@ static int decode_entry(lva_handle *h, const float *post, bool post_on_device, c
     if (cnt[1] == 0) {
       // proactive growth for the next call: linear probing degrades quickly above half full
       if (!h->survivor && h->timing.chain_keys_max * 20ull > (unsigned long long)h->tab_slots * 9ull && h->tab_slots < (1u << 27) &&
-          h->d_tab.ensure((size_t)h->n_slots * h->tab_slots * 2 * 8))
+          h->d_tab.try_grow((size_t)h->n_slots * h->tab_slots * 2 * 8))
         h->tab_slots *= 2;
       break;
     }
     // a chain table filled up: every result of this call is suspect.  Grow the tables and decode again.
     if (attempt == 3 || h->tab_slots >= (1u << 27)) { h->err = "chain table overflow"; return LVA_ERR_OOM; }
-    h->tab_slots *= 4;
     h->timing.table_regrows++;
-    if (!h->d_tab.ensure((size_t)h->n_slots * h->tab_slots * 8)) { h->err = "chain table growth failed"; return LVA_ERR_OOM; }
+    if (!h->d_tab.try_grow((size_t)h->n_slots * h->tab_slots * 4 * 8)) { h->err = "chain table growth failed"; return LVA_ERR_OOM; }
+    h->tab_slots *= 4;
   }
   CK(cudaEventRecord(h->ev[6], h->stream));
   CK(cudaEventSynchronize(h->ev[6]));

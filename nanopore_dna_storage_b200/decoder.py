@@ -32,14 +32,16 @@ class ListDecoder:
 
     def __init__(self, mem_conv: int, rate: int, msg_len: int, list_size: int = 1,
                  max_deviation: int | None = None, rc: bool = False, sync_marker: str = "",
-                 sync_period: int = 0, device: int = 0, max_slots: int = 0, exact_only: bool = False):
+                 sync_period: int = 0, device: int = 0, max_slots: int = 0, exact_only: bool = False,
+                 unfused_band: bool = False):
         self._L = _lib.lib()
         self.mem_conv, self.rate, self.msg_len, self.list_size = mem_conv, rate, msg_len, list_size
         self.rc = rc
         p = _lib.LvaParams(mem_conv, rate, msg_len, list_size,
                            _lib.LVA_DEFAULT_DEVIATION if max_deviation is None else max_deviation,
                            int(rc), sync_marker.encode(), sync_period, device, max_slots,
-                           _lib.LVA_FLAG_EXACT_ONLY if exact_only else 0)
+                           (_lib.LVA_FLAG_EXACT_ONLY if exact_only else 0) |
+                           (_lib.LVA_FLAG_UNFUSED_BAND if unfused_band else 0))
         st = C.c_int(0)
         err = C.create_string_buffer(512)
         self._h = self._L.lva_create(C.byref(p), C.byref(st), err, 512)
@@ -193,8 +195,8 @@ def code_tables(mem_conv: int, rate: int, msg_len: int, rc: bool = False, sync_m
                 valid_value=list(t.valid_value[:P]), history_words=list(t.history_words[:P]))
 
 
-def band(t: int, nblk: int, nstate_pos: int, max_deviation: int):
+def band(t: int, nblk: int, nstate_pos: int, max_deviation: int, unfused: bool = False):
     L = _lib.lib()
     a, b = C.c_uint32(0), C.c_uint32(0)
-    L.lva_band(t, nblk, nstate_pos, max_deviation, C.byref(a), C.byref(b))
+    L.lva_band_ex(t, nblk, nstate_pos, max_deviation, _lib.LVA_FLAG_UNFUSED_BAND if unfused else 0, C.byref(a), C.byref(b))
     return a.value, b.value

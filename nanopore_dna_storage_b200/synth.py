@@ -100,19 +100,6 @@ def frame_message(index: int, payload_bits: np.ndarray, pad: bool) -> np.ndarray
     return np.array(bits, dtype=np.uint8)
 
 
-def check_crc_index(bits, pad: bool):
-    """helper.decode_list_CRC_index for one candidate: (crc_ok, index)."""
-    bits = [int(b) for b in bits]
-    if pad:
-        bits = bits[:-1]
-    n = (len(bits) + 7) // 8 * 8
-    bits = [0] * (n - len(bits)) + bits
-    by = np.packbits(np.array(bits, dtype=np.uint8)).tobytes()
-    ok = crc8(by[:-1]) == by[-1]
-    idx_raw = int.from_bytes(by[:2], "big") & ((1 << INDEX_LEN) - 1)
-    return ok, (PRP_A_INV * (idx_raw - PRP_B)) % (1 << INDEX_LEN)
-
-
 def channel(bases: np.ndarray, rng, sub: float, dele: float, ins: float) -> np.ndarray:
     out, i, n = [], 0, len(bases)
     while True:

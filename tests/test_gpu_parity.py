@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from nanopore_dna_storage_b200 import synth
+from oracle import crc_oracle
 from nanopore_dna_storage_b200.decoder import ListDecoder
 
 pytestmark = pytest.mark.gpu
@@ -94,6 +95,30 @@ def test_flat_posteriors_tie_everywhere(oracle, mem, rate, msg_len, L):
             assert np.array_equal(scores.view(np.uint32), oscores.view(np.uint32))
 
 
+def test_unfused_band_flag_follows_the_unfused_oracle(oracle):
+    """ADVICE: a reference built without FMA contraction bands some reads one row differently; the
+    LVA_FLAG_UNFUSED_BAND handle must then follow the oracle's unfused variant, the default handle the
+    fused one, on reads whose length makes the two differ."""
+    P = 47   # nstate_pos of (mem 6, rate 1, msg_len 40)
+    w = synth.Workload("band", 6, 1, 40, 4, 6, sub=0.01, dele=0.01, ins=0.005, seed=7300, betas=(3.0, 2.0))
+    picked = []
+    for i in range(400):
+        r = synth.make_read(w, i)
+        T = r.post.shape[0]
+        if any(oracle.band_start(t, T, P, 6) != oracle.band_start(t, T, P, 6, unfused=True) for t in range(T)):
+            picked.append(r)
+        if len(picked) == 4:
+            break
+    assert picked, "no read length with a fused/unfused difference found"
+    for unfused in (False, True):
+        with ListDecoder(6, 1, 40, 4, 6, unfused_band=unfused) as dec:
+            got = dec.decode([r.post for r in picked])
+        for r, (bits, scores) in zip(picked, got):
+            st, obits, oscores = oracle.oracle_decode(r.post, 6, 1, 40, 4, 6, unfused_band=unfused)
+            assert st == 0 and bits.shape == obits.shape and np.array_equal(bits, obits)
+            assert np.array_equal(scores.view(np.uint32), oscores.view(np.uint32))
+
+
 def test_more_reads_than_slots(oracle):
     w = synth.Workload("t", 6, 1, 40, 4, 20, sub=0.01, dele=0.01, ins=0.005, seed=7001)
     _compare(oracle, w, 11, exact_only=False, max_slots=4, tag="11 reads in 4 slots")
@@ -126,7 +151,7 @@ def test_gpu_crc_sidecar_matches_python_restatement():
             assert np.array_equal(bits, pbits)
             want_choice = -1
             for e in range(bits.shape[0]):
-                wok, widx = synth.check_crc_index(bits[e], w.pad)
+                wok, widx = crc_oracle.check_crc_index(bits[e], w.pad)
                 assert bool(ok[e]) == wok and int(index[e]) == widx
                 if want_choice < 0 and wok:
                     want_choice = e

