@@ -396,6 +396,8 @@ def main():
                          "algorithmic_bytes_per_step": step_bytes,
                          "avg_launch_us": 1e3 * kernel_ms / max(step_launches, 1),
                          "traffic": tr.get("dram_bytes_per_launch") if tr else None,
+                         "traffic_launch": tr.get("kernel") if tr else None,
+                         "traffic_algorithmic_same_launch": tr.get("algorithmic_bytes_same_launch") if tr else None,
                          "traffic_note": tr.get("note") if tr else None,
                          "alu": {"cand_acs_per_s": cand_acs_per_s, "peak": alu_peak, "frac": cand_acs_per_s / alu_peak,
                                  "note": "SURVEY.md 8(d) issue-slot ceiling: 2 thread-instructions per candidate-ACS"}},
