@@ -392,6 +392,9 @@ def main():
                     "d2h_bytes_per_step": int(host_acc["d2h_bytes"]) // args.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
+                         "hbm_busy_frac": (achieved / peak) * (tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_same_launch"]) if tr else None,
+                         "hbm_busy_note": "frac x (measured DRAM traffic / algorithmic bytes of the committed capture): how busy the "
+                                          "launch keeps HBM; the gap to frac is re-read and partial-write traffic, not useful work",
                          "kernel": "lva_step_fast<LP> (every trellis step launch)",
                          "algorithmic_bytes_per_step": step_bytes,
                          "avg_launch_us": 1e3 * kernel_ms / max(step_launches, 1),

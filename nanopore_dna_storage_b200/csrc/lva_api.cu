@@ -585,6 +585,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *start
   std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return len_of(x) > len_of(y); });
 
   const uint32_t dev2 = 2u * h->max_dev;
+  if (dev2 == 0) return LVA_OK;  // --max-deviation 0: the band [a, a + 0) is empty at every step, no state is ever updated, every list is empty (VCC:677-687)
   float acc_kernel = 0.f, acc_d2h = 0.f;
   std::vector<FinalEntry> fin;
   const uint32_t dec_rows = (uint32_t)std::min<uint64_t>((uint64_t)dev2 > 0 ? dev2 : 1, k.nrows);

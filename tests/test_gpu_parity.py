@@ -119,6 +119,39 @@ def test_unfused_band_flag_follows_the_unfused_oracle(oracle):
             assert np.array_equal(scores.view(np.uint32), oscores.view(np.uint32))
 
 
+def test_chain_table_overflow_is_detected_and_repeated(oracle, monkeypatch):
+    """A chain table that is far too small (1024 slots) must never produce a wrong list: the probe chain
+    runs away, the kernel raises the flag, the call is repeated with larger tables until the read fits."""
+    monkeypatch.setenv("LVA_TAB_LOG2", "10")
+    w = synth.Workload("tab", 6, 5, 130, 8, 20, sub=0.01, dele=0.01, ins=0.005, seed=7400, betas=(3.0, 2.0))
+    reads = synth.make_reads(w, 4)
+    with ListDecoder(6, 5, 130, 8, 20) as dec:
+        got = dec.decode([r.post for r in reads])
+        tm = dec.timing()
+        again = dec.decode([r.post for r in reads])   # the grown tables are kept for the next call
+        tm2 = dec.timing()
+    assert tm["table_regrows"] >= 1 and tm["chain_table_slots"] > 1024 and tm["chain_keys_max"] > 1024
+    assert tm2["table_regrows"] == 0
+    for r, (bits, scores), (b2, s2) in zip(reads, got, again):
+        st, obits, oscores = oracle.oracle_decode(r.post, 6, 5, 130, 8, 20)
+        assert st == 0 and bits.shape == obits.shape and np.array_equal(bits, obits)
+        assert np.array_equal(scores.view(np.uint32), oscores.view(np.uint32))
+        assert np.array_equal(bits, b2) and np.array_equal(scores.view(np.uint32), s2.view(np.uint32))
+
+
+def test_zero_and_tiny_deviation(oracle):
+    """--max-deviation 0 (empty band: every list empty, like the reference) and 1 (a 3-row window)."""
+    w = synth.Workload("dev", 6, 1, 40, 4, 20, sub=0.01, dele=0.01, ins=0.005, seed=7500)
+    reads = synth.make_reads(w, 3)
+    for dev in (0, 1, 2):
+        with ListDecoder(6, 1, 40, 4, dev) as dec:
+            got = dec.decode([r.post for r in reads])
+        for r, (bits, scores) in zip(reads, got):
+            st, obits, oscores = oracle.oracle_decode(r.post, 6, 1, 40, 4, dev)
+            assert st == 0 and bits.shape == obits.shape and np.array_equal(bits, obits), dev
+            assert np.array_equal(scores.view(np.uint32), oscores.view(np.uint32))
+
+
 def test_more_reads_than_slots(oracle):
     w = synth.Workload("t", 6, 1, 40, 4, 20, sub=0.01, dele=0.01, ins=0.005, seed=7001)
     _compare(oracle, w, 11, exact_only=False, max_slots=4, tag="11 reads in 4 slots")
