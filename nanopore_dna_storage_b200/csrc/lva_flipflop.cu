@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/lva_b200.h"
+#include "device_scratch.hpp"
 
 namespace {
 
@@ -96,33 +97,27 @@ int run(int32_t device, const float *trans, bool on_device, const uint64_t *offs
   if (!trans || !offs || !out) return LVA_ERR_BAD_ARG;
   for (uint32_t i = 0; i < n_reads; i++)
     if (offs[i + 1] < offs[i] || offs[i + 1] - offs[i] > 0xffffffffull) return LVA_ERR_BAD_ARG;
-  if (cudaSetDevice(device) != cudaSuccess) return LVA_ERR_NO_DEVICE;
+  if (device < 0 || device >= 16 || cudaSetDevice(device) != cudaSuccess) return LVA_ERR_NO_DEVICE;
   const uint64_t first = offs[0], nblk = offs[n_reads] - first;
   std::vector<uint64_t> rel(n_reads + 1);
   for (uint32_t i = 0; i <= n_reads; i++) rel[i] = offs[i] - first;
-  float *d_trans = nullptr, *d_out = nullptr, *d_fwd = nullptr;
-  uint64_t *d_offs = nullptr;
-  int rc = LVA_OK;
-  auto fail = [&](int code) { rc = code; };
-  if (cudaMalloc(&d_offs, (n_reads + 1) * 8) != cudaSuccess || cudaMalloc(&d_fwd, (nblk + n_reads) * 32 + 32) != cudaSuccess) fail(LVA_ERR_OOM);
-  if (rc == LVA_OK && !on_device &&
-      (cudaMalloc(&d_trans, nblk * 160 + 16) != cudaSuccess || cudaMalloc(&d_out, nblk * 160 + 16) != cudaSuccess)) fail(LVA_ERR_OOM);
-  if (rc == LVA_OK) {
-    cudaMemcpy(d_offs, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice);
-    const float *tin = on_device ? trans + first * 40 : d_trans;
-    float *tout = on_device ? out + first * 40 : d_out;
-    if (!on_device) cudaMemcpy(d_trans, trans + first * 40, nblk * 160, cudaMemcpyHostToDevice);
-    const uint32_t groups_per_block = 128 / 8;
-    flipflop_posteriors<<<(n_reads + groups_per_block - 1) / groups_per_block, 128>>>(tin, d_offs, n_reads, tout, d_fwd);
-    if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) fail(LVA_ERR_CUDA);
-    if (rc == LVA_OK && !on_device && cudaMemcpy(out + first * 40, d_out, nblk * 160, cudaMemcpyDeviceToHost) != cudaSuccess)
-      fail(LVA_ERR_CUDA);
-  }
-  cudaFree(d_offs);
-  cudaFree(d_fwd);
-  cudaFree(d_trans);
-  cudaFree(d_out);
-  return rc;
+  lva::DeviceScratch &S = lva::scratch_for(device);
+  std::lock_guard<std::mutex> hold(S.mu);
+  if (!S.ready()) return LVA_ERR_CUDA;
+  uint64_t *d_offs = (uint64_t *)S.get(0, (n_reads + 1) * 8);
+  float *d_fwd = (float *)S.get(1, (nblk + n_reads) * 32 + 32);
+  float *d_trans = on_device ? nullptr : (float *)S.get(2, nblk * 160 + 16);
+  float *d_out = on_device ? nullptr : (float *)S.get(3, nblk * 160 + 16);
+  if (!d_offs || !d_fwd || (!on_device && (!d_trans || !d_out))) return LVA_ERR_OOM;
+  cudaMemcpyAsync(d_offs, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, S.stream);
+  const float *tin = on_device ? trans + first * 40 : d_trans;
+  float *tout = on_device ? out + first * 40 : d_out;
+  if (!on_device) cudaMemcpyAsync(d_trans, trans + first * 40, nblk * 160, cudaMemcpyHostToDevice, S.stream);
+  const uint32_t groups_per_block = 128 / 8;
+  flipflop_posteriors<<<(n_reads + groups_per_block - 1) / groups_per_block, 128, 0, S.stream>>>(tin, d_offs, n_reads, tout, d_fwd);
+  if (cudaGetLastError() != cudaSuccess) return LVA_ERR_CUDA;
+  if (!on_device) cudaMemcpyAsync(out + first * 40, d_out, nblk * 160, cudaMemcpyDeviceToHost, S.stream);
+  return cudaStreamSynchronize(S.stream) == cudaSuccess ? LVA_OK : LVA_ERR_CUDA;
 }
 
 }  // namespace

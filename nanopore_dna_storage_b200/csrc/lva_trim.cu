@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/lva_b200.h"
+#include "device_scratch.hpp"
 
 namespace {
 
@@ -143,12 +144,6 @@ bool reverse_complement(const char *s, uint32_t n, uint8_t *out) {  // helper.py
   return true;
 }
 
-struct Buf {
-  void *p = nullptr;
-  ~Buf() { if (p) cudaFree(p); }
-  bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 16) == cudaSuccess; }
-};
-
 }  // namespace
 
 extern "C" int lva_trim_batch(int32_t device, const char *basecalls, const uint64_t *base_offsets,
@@ -187,16 +182,20 @@ extern "C" int lva_trim_batch(int32_t device, const char *basecalls, const uint6
     if (i && boff[i] - boff[i - 1] > 0x7fffffffull) return LVA_ERR_BAD_ARG;
     if (i) max_len = std::max<uint32_t>(max_len, (uint32_t)(boff[i] - boff[i - 1]));
   }
-  Buf d_bases, d_boff, d_trans, d_toff, d_best, d_out;
+  if (device < 0 || device >= 16) return LVA_ERR_NO_DEVICE;
+  lva::DeviceScratch &S = lva::scratch_for(device);
+  std::lock_guard<std::mutex> hold(S.mu);
+  if (!S.ready()) return LVA_ERR_CUDA;
+  struct Ref { void *p; } d_bases{S.get(0, nb + 16)}, d_boff{S.get(1, (n_reads + 1) * 8)}, d_trans{S.get(2, nt * 4 + 16)},
+      d_toff{S.get(3, (n_reads + 1) * 8)}, d_best{S.get(4, (size_t)n_reads * 4 * 8)};
   const size_t out_words = (size_t)n_reads * 8;
-  if (!d_bases.alloc(nb) || !d_boff.alloc((n_reads + 1) * 8) || !d_trans.alloc(nt * 4) || !d_toff.alloc((n_reads + 1) * 8) ||
-      !d_best.alloc((size_t)n_reads * 4 * 8) || !d_out.alloc(out_words * 4))
-    return LVA_ERR_OOM;
-  cudaMemcpy(d_bases.p, basecalls + base_offsets[0], nb, cudaMemcpyHostToDevice);
-  cudaMemcpy(d_boff.p, boff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice);
-  cudaMemcpy(d_trans.p, trans + trans_offsets[0], nt * 4, cudaMemcpyHostToDevice);
-  cudaMemcpy(d_toff.p, toff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice);
-  cudaMemset(d_best.p, 0xff, (size_t)n_reads * 4 * 8);
+  Ref d_out{S.get(5, out_words * 4)};
+  if (!d_bases.p || !d_boff.p || !d_trans.p || !d_toff.p || !d_best.p || !d_out.p) return LVA_ERR_OOM;
+  cudaMemcpyAsync(d_bases.p, basecalls + base_offsets[0], nb, cudaMemcpyHostToDevice, S.stream);
+  cudaMemcpyAsync(d_boff.p, boff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, S.stream);
+  cudaMemcpyAsync(d_trans.p, trans + trans_offsets[0], nt * 4, cudaMemcpyHostToDevice, S.stream);
+  cudaMemcpyAsync(d_toff.p, toff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, S.stream);
+  cudaMemsetAsync(d_best.p, 0xff, (size_t)n_reads * 4 * 8, S.stream);
   a.bases = (const uint8_t *)d_bases.p;
   a.base_off = (const uint64_t *)d_boff.p;
   a.trans = (const uint32_t *)d_trans.p;
@@ -215,12 +214,13 @@ extern "C" int lva_trim_batch(int32_t device, const char *basecalls, const uint6
     const uint32_t nr = std::min<uint32_t>(65535u, n_reads - r0);
     b.base_off = a.base_off + r0;
     b.best = a.best + (size_t)r0 * 4;
-    trim_search<<<dim3((max_win + 127) / 128, nr, 4), 128>>>(b);
+    trim_search<<<dim3((max_win + 127) / 128, nr, 4), 128, 0, S.stream>>>(b);
   }
-  trim_finish<<<(n_reads + 127) / 128, 128>>>(a);
+  trim_finish<<<(n_reads + 127) / 128, 128, 0, S.stream>>>(a);
   if (cudaGetLastError() != cudaSuccess) return LVA_ERR_CUDA;
   std::vector<int32_t> host(out_words);
-  if (cudaMemcpy(host.data(), d_out.p, out_words * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return LVA_ERR_CUDA;
+  cudaMemcpyAsync(host.data(), d_out.p, out_words * 4, cudaMemcpyDeviceToHost, S.stream);
+  if (cudaStreamSynchronize(S.stream) != cudaSuccess) return LVA_ERR_CUDA;
   memcpy(out_start, host.data(), (size_t)n_reads * 4);
   memcpy(out_end, host.data() + n_reads, (size_t)n_reads * 4);
   memcpy(out_rc, host.data() + 2 * (size_t)n_reads, (size_t)n_reads * 4);

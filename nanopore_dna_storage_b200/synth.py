@@ -228,6 +228,7 @@ def workloads() -> dict:
         "C4r3": Workload("C4 m8 r3/4 msg181 L8", 8, 3, 181, 8, seed=0x5EED0005, **ch),
         "C4r4": Workload("C4 m8 r4/5 msg180 L8", 8, 4, 180, 8, seed=0x5EED0006, **ch),
         "C4r7": Workload("C4 m8 r7/8 msg181 L8", 8, 7, 181, 8, seed=0x5EED0007, **ch),
+        "C4r2L64": Workload("m8 r2/3 msg180 L64 (the paper's list size for m=8)", 8, 2, 180, 64, seed=0x5EED0009, **ch),
         "C5": Workload("C5 m11 r5/6 msg180 L16 fwd+rc", 11, 5, 180, 16, seed=0x5EED0008,
                        rc_fraction=0.5, **ch),
     }
