@@ -267,6 +267,8 @@ __device__ __noinline__ int exact_merge(const uint32_t *src, uint32_t *mine, con
   }
   heap_make(H, n);
   int l = 0;
+  uint32_t sigs[(LP + 3) / 4];
+  for (int r = 0; r < (LP + 3) / 4; r++) sigs[r] = 0;
   while (n > 0 && l < L) {
     heap_pop(H, n);
     n--;
@@ -274,12 +276,24 @@ __device__ __noinline__ int exact_merge(const uint32_t *src, uint32_t *mine, con
     const int k = (int)(ht[n] >> 8), j = (int)(ht[n] & 255u);
     uint32_t id, pt;
     M.identity(k, j, id, pt);
+    // de-duplicate against the accepted entries: one-byte signatures, four per word, screen them;
+    // only a signature match is compared in full (list sizes up to 64 make the plain scan the cost)
+    const uint32_t sig = (((id ^ pt) * 0x01010101u) >> 25) | 0x80u;
     bool dup = false;
-    for (int i = 0; i < l && !dup; i++) dup = mine[(LP + i) * NT] == id && mine[(2 * LP + i) * NT] == pt;
+    for (int r = 0; 4 * r < l && !dup; r++) {
+      const uint32_t x = sigs[r] ^ (sig * 0x01010101u);
+      uint32_t m = (x - 0x01010101u) & ~x & 0x80808080u;  // may also flag the byte above a true match: verified below
+      while (m != 0 && !dup) {
+        const int i = 4 * r + ((__ffs(m) - 1) >> 3);
+        m &= m - 1u;
+        dup = i < l && mine[(LP + i) * NT] == id && mine[(2 * LP + i) * NT] == pt;
+      }
+    }
     if (!dup) {
       mine[l * NT] = __float_as_uint(sc);
       mine[(LP + l) * NT] = id;
       mine[(2 * LP + l) * NT] = pt;
+      sigs[l >> 2] |= sig << (8 * (l & 3));
       l++;
     }
     if (j == L - 1) continue;
