@@ -663,8 +663,6 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *start
     a.tab_mask = h->tab_slots - 1;
     a.dev2 = dev2;
     a.code_slot = h->code_slot;
-    a.row_lo = 0;
-    a.row_hi = k.nrows;
     { static const char *dbg_env = getenv("LVA_DBG"); a.dbg = dbg_env ? (uint32_t)atoi(dbg_env) : 0u; }
     ClearArgs clr{};
     clr.state = a.state;
@@ -679,18 +677,22 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *start
       a.t = t;
       uint32_t span = 0;
       bool any_clear = false;
-      for (uint32_t s = 0; s < active; s++) {
-        const uint32_t st = band[rd[s].band_off + t], en = band_end(st, k.nrows, h->max_dev);
-        span = std::max(span, en - st);
-        a.band_a[s] = (uint16_t)st;
-        a.band_slot[s] = (uint16_t)(st % h->window);
-        a.post_blk[s] = (uint32_t)(rd[s].post_block + t);
-        clr.row[s] = 0xFFFFu;
-        if (!h->survivor && t > 0 && en > 0) {
-          // a row entering the band re-uses a window slot: wipe it first (lva_clear_rows); the band
-          // end grows by at most one row per step (T >= nstate_pos + 1)
-          const uint32_t en_prev = band_end(band[rd[s].band_off + t - 1], k.nrows, h->max_dev);
-          if (en > en_prev && en - 1 >= h->window) { clr.row[s] = (uint16_t)(en - 1); any_clear = true; }
+      if (h->survivor) {
+        span = std::min<uint32_t>(dev2, k.nrows);  // lva_step_l1 reads its per-read control data from the device tables
+      } else {
+        for (uint32_t s = 0; s < active; s++) {
+          const uint32_t st = band[rd[s].band_off + t], en = band_end(st, k.nrows, h->max_dev);
+          span = std::max(span, en - st);
+          a.band_a[s] = (uint16_t)st;
+          a.band_slot[s] = (uint16_t)(st % h->window);
+          a.post_blk[s] = (uint32_t)(rd[s].post_block + t);
+          clr.row[s] = 0xFFFFu;
+          if (t > 0 && en > 0) {
+            // a row entering the band re-uses a window slot: wipe it first (lva_clear_rows); the band
+            // end grows by at most one row per step (T >= nstate_pos + 1)
+            const uint32_t en_prev = band_end(band[rd[s].band_off + t - 1], k.nrows, h->max_dev);
+            if (en > en_prev && en - 1 >= h->window) { clr.row[s] = (uint16_t)(en - 1); any_clear = true; }
+          }
         }
       }
       if (span == 0) continue;

@@ -80,11 +80,10 @@ struct StepArgs {
   unsigned long long parity_words;  // words of one parity buffer (W * row_words)
   unsigned long long nid_parity_words;
   const float *post;
-  unsigned long long *counters;   // [0] exact fallbacks, [1] table overflow flag, [2] table inserts
+  unsigned long long *counters;   // [0] exact fallbacks, [1] chain table overflow flag, [8 + slot] keys of that read's chain table
   uint32_t row_words, piece_words;
   uint32_t tab_mask;              // tab_slots - 1
   uint32_t t, dev2, code_slot;
-  uint32_t row_lo, row_hi;        // rows this launch is responsible for
   uint32_t dbg;                   // developer switches (LVA_DBG), 0 in production: bit 1 data movement only, bit 4 no stores, bits 8.. L2 prefetch distance in CTAs
   uint32_t post_blk[kMaxSlots];   // per active slot: index of the posterior block of this step
   uint16_t band_a[kMaxSlots];     // per active slot: first in-band row of this step (VCC:677-678)

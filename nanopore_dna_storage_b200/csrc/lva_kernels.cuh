@@ -337,8 +337,7 @@ __global__ void __launch_bounds__(TG * 8) lva_step_generic(const StepArgs A) {
   const uint32_t a = A.band_a[z];
   uint32_t bend = a + A.dev2;
   if (bend > K.nrows) bend = K.nrows;
-  if (bend > A.row_hi) bend = A.row_hi;  // a launch may be restricted to rows [row_lo, row_hi)
-  const uint32_t p = (a > A.row_lo ? a : A.row_lo) + blockIdx.y;
+  const uint32_t p = a + blockIdx.y;
   if (p >= bend) return;
   const int tid = threadIdx.x;
   const uint32_t tile = blockIdx.x;
