@@ -3,9 +3,10 @@
 make_golden.py: decoded lists of the UNMODIFIED reference (oracle/_ref, compiled in place from
 /root/reference) on seeded synthetic reads.  This batch covers what the first one left open:
 
-  * the bench workload itself: reads 0..15 of synth.workloads()["C2"] (five of them beta = 3
-    "hard" reads) plus three reads whose length is a multiple of 29 (fused-band hazard,
-    T = 493 / 522) -- bench.py compares its GPU output with these outside the timed region;
+  * the bench workload itself: reads 0..63 of synth.workloads()["C2"] -- the whole batch bench.py
+    decodes on one GPU (a quarter of them beta = 3 "hard" reads) -- plus three reads whose length
+    is a multiple of 29 (fused-band hazard, T = 493 / 522); bench.py compares its GPU output with
+    these outside the timed region;
   * C3 at the paper's msg_len 100 (m = 14, 16384 x 8 states per row) and one read at msg_len 180;
   * C5 (L = 16) in BOTH orientations at full size;
   * list sizes above 16 (L = 32, L = 64 at m = 8, the paper's list size for m = 8).
@@ -38,6 +39,7 @@ CASES = [
     ("r2 m8 r5/6 msg180 L64 rc", M8L64RC, [2]),
     ("r2 C5 m11 r5/6 msg180 L16 fwd+rc", C5, [0, 1, 2]),
     ("r2 C2 bench reads", C2, list(range(16)) + [169, 214, 342]),
+    ("r2 C2 bench reads", C2, list(range(16, 64))),   # the rest of rank 0's bench batch: every benchmarked read has a fixture
     ("r2 C3 m14 r1/2 msg100 L8", C3, [0, 1]),
     ("r2 C3 m14 r1/2 msg180 L8", C3L, [0]),
 ]
