@@ -133,6 +133,8 @@ typedef struct lva_code_tables {
   uint32_t pos2msg[260];   /* st_pos2msg_pos */
   uint32_t valid_mask[260], valid_value[260]; /* is_valid_state (VCC:944-978) as (c & mask) == value per row */
   uint8_t history_words[260];                 /* 32-bit message-history words carried per list entry per row */
+  uint8_t first_run_row[260];                 /* 1: some message prefix reaches this row with all its bases equal (row 0 included):
+                                                 only there can one message sit in two crf states of a conv state */
 } lva_code_tables;
 int lva_get_code_tables(uint32_t mem_conv, uint32_t rate, uint32_t msg_len, int32_t rc,
                         const char *sync_marker, uint32_t sync_period, lva_code_tables *out);
@@ -169,6 +171,7 @@ typedef struct lva_timing {
   uint64_t chain_keys_max;  /* ... the most any one read needed */
   uint64_t chain_table_slots; /* slots of one read's chain table */
   uint64_t table_regrows;   /* times the call was repeated with larger chain tables */
+  uint64_t structure_check_failures; /* developer check (LVA_DBG bit 3) of the two-stage merge's precondition; 0 */
 } lva_timing;
 int lva_get_timing(const lva_handle *h, lva_timing *out);
 

@@ -30,7 +30,8 @@ class LvaCodeTables(C.Structure):
     _fields_ = [("G", C.c_uint32 * 2), ("initial_state", C.c_uint32), ("final_state", C.c_uint32),
                 ("punc_len", C.c_uint32), ("nstate_pos", C.c_uint32), ("punc", C.c_uint8 * 16),
                 ("pos2msg", C.c_uint32 * 260), ("valid_mask", C.c_uint32 * 260),
-                ("valid_value", C.c_uint32 * 260), ("history_words", C.c_uint8 * 260)]
+                ("valid_value", C.c_uint32 * 260), ("history_words", C.c_uint8 * 260),
+                ("first_run_row", C.c_uint8 * 260)]
 
 
 class LvaWork(C.Structure):
@@ -42,7 +43,8 @@ class LvaTiming(C.Structure):
                 ("d2h_ms", C.c_float), ("launches", C.c_uint64), ("step_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("exact_fallbacks", C.c_uint64),
                 ("chain_inserts", C.c_uint64), ("chain_keys_max", C.c_uint64),
-                ("chain_table_slots", C.c_uint64), ("table_regrows", C.c_uint64)]
+                ("chain_table_slots", C.c_uint64), ("table_regrows", C.c_uint64),
+                ("structure_check_failures", C.c_uint64)]
 
 
 def build(verbose: bool = False) -> None:

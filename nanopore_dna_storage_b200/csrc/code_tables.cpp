@@ -143,7 +143,55 @@ int build_code_spec(CodeSpec &k, uint32_t mem, uint32_t rate, uint32_t msg_len, 
     }
     k.chunk_of[p] = (uint8_t)k.nchunks;
   }
+  first_run_rows(k);
   return kCodeOk;
+}
+
+uint32_t host_emitted_base(const CodeSpec &k, uint32_t blk, uint32_t c_src, uint32_t in1, uint32_t in2) {
+  const uint32_t r = k.rc ? 1u : 0u;
+  auto par = [](uint32_t v) { return (uint32_t)__builtin_parity(v); };
+  const uint32_t w1 = c_src | (in1 << k.mem);
+  const uint32_t o0 = par(w1 & k.G[0]) ^ r, o1 = par(w1 & k.G[1]) ^ r;
+  if (blk == 0) return 2 * o0 + o1;
+  const uint32_t w2 = (w1 >> 1) | (in2 << k.mem);
+  const uint32_t o2 = par(w2 & k.G[0]) ^ r, o3 = par(w2 & k.G[1]) ^ r;
+  if (blk == 1) return r ? 2 * o2 + o1 : 2 * o1 + o2;
+  if (blk == 2) return r ? 2 * o3 + o0 : 2 * o0 + o3;
+  return r ? 2 * o3 + o1 : 2 * o1 + o3;
+}
+
+// Rows a message prefix can reach with all its bases equal (CodeSpec::first_run): per base b, the set of
+// conv states of row q reached from the start state through valid states by transitions that all emit b.
+void first_run_rows(CodeSpec &k) {
+  std::vector<uint8_t> cur[4], nxt[4];
+  for (int b = 0; b < 4; b++) {
+    cur[b].assign(k.nconv, 0);
+    cur[b][k.init] = 1;
+  }
+  for (uint32_t p = 0; p < k.nrows; p++) k.first_run[p] = 0;
+  k.first_run[0] = 1;
+  for (uint32_t q = 1; q < k.nrows; q++) {
+    const uint32_t sh = k.shift[q];
+    bool any = false;
+    for (uint32_t b = 0; b < 4; b++) {
+      nxt[b].assign(k.nconv, 0);
+      for (uint32_t c = 0; c < k.nconv; c++) {
+        if (!cur[b][c]) continue;
+        for (uint32_t in = 0; in < (1u << sh); in++) {
+          const uint32_t in1 = in & 1u, in2 = in >> 1;
+          uint32_t c2 = (c | (in1 << k.mem)) >> 1;
+          if (sh == 2) c2 = (c2 | (in2 << k.mem)) >> 1;
+          if ((c2 & k.vmask[q]) != k.vval[q]) continue;
+          if (host_emitted_base(k, k.block[q], c, in1, in2) != b) continue;
+          nxt[b][c2] = 1;
+          any = true;
+        }
+      }
+      cur[b].swap(nxt[b]);
+    }
+    if (!any) break;
+    k.first_run[q] = 1;
+  }
 }
 
 uint32_t band_start(uint32_t t, uint32_t nblk, uint32_t nrows, uint32_t max_deviation, bool fused) {

@@ -56,12 +56,23 @@ struct CodeSpec {
   uint8_t plen[kMaxRows] = {0};     // bits in the partial chunk at row p (<= 32)
   uint8_t boundary[kMaxRows] = {0}; // 1: the partial chunk of row p is complete; a move out of it starts a new one
   uint8_t chunk_of[kMaxRows] = {0}; // number of completed chunks behind an entry of row p
+  // first_run[p] = 1: some message prefix reaches row p with ALL its bases equal (row 0 counts).  All eight
+  // crf states start at row 0 (VCC:657-663), so whether such a path sits in the flip or the flop state of
+  // its base is open: the same message can be in two crf lists of one conv state.  Everywhere else the crf
+  // state follows from the base sequence (flip on a new base, flip/flop alternating inside a run).
+  uint8_t first_run[kMaxRows] = {0};
   uint32_t nchunks = 0;             // completed chunks behind an entry of the last row
   uint8_t chunk_len[16] = {0};      // bits of completed chunk k
 };
 
 int build_code_spec(CodeSpec &k, uint32_t mem, uint32_t rate, uint32_t msg_len, bool rc,
                     const std::string &marker, uint32_t period);
+
+// base emitted by the conv transition out of c_src under puncturing block blk with input bits in1 (, in2)
+// (VCC:440-448 and the block table of VCC:860-942); the kernels' emitted_base() is the same function
+uint32_t host_emitted_base(const CodeSpec &k, uint32_t blk, uint32_t c_src, uint32_t in1, uint32_t in2);
+
+void first_run_rows(CodeSpec &k);  // fills CodeSpec::first_run (called by build_code_spec)
 
 // band start of time step t (VCC:677-679).  fused = true: t/nblk*nstate_pos - max_deviation evaluated
 // as ONE fused multiply-subtract, which is what g++ -O3 emits for the reference on FMA hardware

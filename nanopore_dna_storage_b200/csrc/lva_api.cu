@@ -116,21 +116,6 @@ uint32_t next_pow2(uint32_t v) {
   return p;
 }
 
-// host mirror of emitted_base(): used once per handle to verify the butterfly structure the
-// kernels rely on (every base has at most one conv predecessor)
-uint32_t host_emitted_base(const CodeSpec &k, uint32_t blk, uint32_t c_src, uint32_t in1, uint32_t in2) {
-  const uint32_t r = k.rc ? 1u : 0u;
-  auto par = [](uint32_t v) { return (uint32_t)__builtin_parity(v); };
-  const uint32_t w1 = c_src | (in1 << k.mem);
-  const uint32_t o0 = par(w1 & k.G[0]) ^ r, o1 = par(w1 & k.G[1]) ^ r;
-  if (blk == 0) return 2 * o0 + o1;
-  const uint32_t w2 = (w1 >> 1) | (in2 << k.mem);
-  const uint32_t o2 = par(w2 & k.G[0]) ^ r, o3 = par(w2 & k.G[1]) ^ r;
-  if (blk == 1) return r ? 2 * o2 + o1 : 2 * o1 + o2;
-  if (blk == 2) return r ? 2 * o3 + o0 : 2 * o0 + o3;
-  return r ? 2 * o3 + o1 : 2 * o1 + o3;
-}
-
 bool butterfly_structure_ok(const CodeSpec &k) {
   for (uint32_t blk = 0; blk < 4; blk++) {
     bool used = false;
@@ -182,7 +167,7 @@ size_t generic_smem_bytes(uint32_t LP, uint32_t tg) {
   return 256 + ((size_t)24 * LP * tg + (size_t)3 * LP * tg * 8) * 4;
 }
 
-constexpr size_t kCounterBytes = (8 + kMaxSlots) * sizeof(unsigned long long);  // [0] fallbacks [1] overflow [8+z] keys of slot z
+constexpr size_t kCounterBytes = (8 + kMaxSlots) * sizeof(unsigned long long);  // [0] fallbacks [1] overflow [2] structure check failures [8+z] keys of slot z
 
 struct FinalEntry {
   float score;
@@ -387,6 +372,7 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
       r.src_nid_slot = p > 0 ? slot_of[p - 1] : 0;
       r.app_pos = (p > 0 && !r.post_boundary) ? k.plen[p - 1] : 0;
       r.nohist = (k.plen[p] == 0 && k.chunk_of[p] == 0) ? 1 : 0;
+      r.xdup = (p == 0 || k.first_run[p - 1]) ? 1 : 0;  // the source row may hold one message in two crf lists
       if (p > 0) {  // linear map low predecessor bits -> emitted base (verified bijective by butterfly_structure_ok)
         const uint32_t b0 = host_emitted_base(k, k.block[p], 0, 0, 0);
         for (uint32_t xy = 0; xy < (1u << k.shift[p]); xy++) {
@@ -531,6 +517,7 @@ int lva_get_code_tables(uint32_t mem_conv, uint32_t rate, uint32_t msg_len, int3
     out->valid_mask[p] = k.vmask[p];
     out->valid_value[p] = k.vval[p];
     out->history_words[p] = k.idwords[p];
+    out->first_run_row[p] = k.first_run[p];
   }
   return LVA_OK;
 }
@@ -878,9 +865,10 @@ static int decode_entry(lva_handle *h, const float *post, bool post_on_device, c
     h->timing.chain_keys_max = 0;
     int st = decode_core(h, d_post, starts, ends, n_reads, crc, out_bits, out_scores, out_counts, out_status);
     if (st != LVA_OK) return st;
-    unsigned long long cnt[2] = {0, 0};
+    unsigned long long cnt[3] = {0, 0, 0};
     CK(cudaMemcpy(cnt, h->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost));
     h->timing.exact_fallbacks = cnt[0];
+    h->timing.structure_check_failures = cnt[2];
     h->timing.chain_table_slots = h->tab_slots;
     if (cnt[1] == 0) {
       // proactive growth for the next call: linear probing degrades quickly above half full

@@ -51,7 +51,8 @@ struct RowDev {
   // The base a conv transition emits is XOR-linear in the predecessor's low `shift` bits xy:
   // base(c', xy) = base(c', 0) ^ lin[xy].  inv_lin packs, for t = 0..3, the xy with lin[xy] == t
   // (2 bits each; one-bit steps: only t in {0, lin[1]} exist) and lin1 = lin[1] for one-bit steps.
-  uint8_t inv_lin, lin1, pad0;
+  uint8_t inv_lin, lin1;
+  uint8_t xdup;            // 1: the source row p-1 may hold one message in two crf lists (first_run_rows): pop-by-pop merge
 };
 
 struct CodeDev {
@@ -80,11 +81,11 @@ struct StepArgs {
   unsigned long long parity_words;  // words of one parity buffer (W * row_words)
   unsigned long long nid_parity_words;
   const float *post;
-  unsigned long long *counters;   // [0] exact fallbacks, [1] chain table overflow flag, [8 + slot] keys of that read's chain table
+  unsigned long long *counters;   // [0] exact fallbacks, [1] chain table overflow flag, [2] structure check failures (LVA_DBG bit 3), [8 + slot] keys of that read's chain table
   uint32_t row_words, piece_words;
   uint32_t tab_mask;              // tab_slots - 1
   uint32_t t, dev2, code_slot;
-  uint32_t dbg;                   // developer switches (LVA_DBG), 0 in production: bit 1 data movement only, bit 4 no stores, bits 8.. L2 prefetch distance in CTAs
+  uint32_t dbg;                   // developer switches (LVA_DBG), 0 in production: bit 1 data movement only, bit 2 pop-by-pop merge on every row, bit 3 check the two-stage merge's structural claim, bit 4 no stores
   uint32_t post_blk[kMaxSlots];   // per active slot: index of the posterior block of this step
   uint16_t band_a[kMaxSlots];     // per active slot: first in-band row of this step (VCC:677-678)
   uint16_t band_slot[kMaxSlots];  // per active slot: band_a % window (the window slot of the first in-band row)

@@ -252,6 +252,194 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL>
   return tie ? -1 : l;
 }
 
+// Two-stage merge (list size == slot count <= 8; every row whose source row cannot hold one message in
+// two crf lists -- RowDev::xdup, code_tables.cpp first_run_rows()).
+//
+// A message reaches a state at most twice per step: through the state's own (stay) list A and through
+// ONE predecessor list: the crf state a message sits in at row p-1 follows from its base sequence
+// (last base; flip or flop by the parity of the closing homopolymer run), the only freedom being the
+// parity of the FIRST run, because all eight crf states start at row 0 (VCC:657-663).  Away from those
+// first rows the move-in candidates B are pairwise distinct, so
+//   stage B  the LP best move-in candidates are the first LP pops of a plain 7-way merge -- no
+//            de-duplication, every lane pops in lock step, exactly LP trips (flop targets have one
+//            predecessor list: nothing to merge).  Later move-in candidates can never be accepted:
+//            LP distinct messages with better metrics come before them;
+//   stage T  twins: each of the LP own entries is compared with the LP move-in candidates, held in
+//            registers (exact two-word compare, no signatures, no divergence); of a twin pair the entry
+//            with the lower metric is marked dropped;
+//   stage F  the survivors of A and B are disjoint and sorted: a two-way merge writes the new list, at
+//            most LP trips, in lock step.
+// Without ties this is the reference's list: sort all candidates by metric, keep the first occurrence of
+// every message, stop at LP.  Ties (equal metrics of successive pops from different lists in stage B,
+// of the candidate behind the last one kept, of a twin pair, of the two heads in stage F) send the state
+// to exact_merge() as before: a superset of the cases where libstdc++'s heap order could show.
+// Returns the number of accepted entries, or -1 on a tie.
+template <int LP, int NL>
+__device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP, NL> &V, AcceptLog<LP> &log, unsigned am,
+                                               bool check, unsigned long long *counters) {
+  static_assert(LP <= 8, "stage T keeps 3*LP words of move-in candidates in registers");
+  using View = ListView<LP, NL>;
+  constexpr uint32_t SS = View::SS, LS = View::LS, PS = View::PS, GP = 64u * LP;
+  constexpr uint32_t FULL = (1u << LP) - 1u;
+  const float NEG = neg_inf();
+  bool tie = false;
+  unsigned long long desc = 0;  // byte e = (tile crf << 4 | slot) of the e-th best move-in candidate
+  int nB = LP;                  // live move-in candidates among them
+
+  // ---- stage B ----
+  if constexpr (NL == 8) {
+    float h[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = i == V.s ? NEG : lds_f32(V.srcg + (uint32_t)i * LS) + lds_f32(V.wrow + 4u * (uint32_t)i);
+    float best, last_m = __int_as_float(0x7f800000);  // +inf: never equals a metric
+    int i, last_i = -1;
+    select_head<8>(h, best, i);
+    uint32_t ptrs = 0;
+    nB = 0;
+    int e = 0;
+#pragma unroll 1
+    for (; e < LP; e++) {
+      const bool live = best != NEG;
+      if (!__any_sync(am, live)) break;
+      const int j = (ptrs >> (4 * i)) & 15;
+      desc = (desc >> 8) | ((unsigned long long)(uint32_t)((i << 4) | j) << (8 * LP - 8));
+      nB += live ? 1 : 0;
+      tie = tie || (live && best == last_m && i != last_i);
+      last_m = best;
+      last_i = i;
+      float nh = NEG;
+      if (live && j + 1 < LP) {
+        nh = lds_f32(V.srcg + (uint32_t)i * LS + (uint32_t)(j + 1) * SS) + lds_f32(V.wrow + 4u * (uint32_t)i);
+        ptrs += 1u << (4 * i);
+      }
+#pragma unroll
+      for (int i2 = 0; i2 < 8; i2++) h[i2] = (i2 == i) ? nh : h[i2];
+      select_head<8>(h, best, i);
+    }
+    desc >>= 8 * (LP - e);
+    tie = tie || (best != NEG && best == last_m);  // the candidate behind the LP-th: which of the two is in B?
+  } else {
+    desc = (0x0706050403020100ull | (0x1010101010101010ull * (unsigned long long)(uint32_t)(V.s - 4))) & (~0ull >> (64 - 8 * LP));
+  }
+
+  // ---- the move-in candidates, into registers ----
+  float mB[LP];
+  uint32_t idB[LP], ptB[LP];
+#pragma unroll
+  for (int e = 0; e < LP; e++) {
+    const uint32_t d = (uint32_t)(desc >> (8 * e)) & 0xffu, crf = d >> 4;
+    const uint32_t addr = V.srcg + crf * LS + (d & 15u) * SS;
+    const float m = lds_f32(addr) + lds_f32(V.wrow + 4u * crf);
+    const bool live = e < nB && m != NEG;
+    mB[e] = live ? m : NEG;
+    // a dead slot may still hold the identity of an entry that lives elsewhere: it must match nothing
+    idB[e] = live ? lds_u32(addr + PS) : 0xffffffffu;  // no chain id has this value (table slots < 2^27, kRootId)
+    ptB[e] = (lds_u32(addr + 2 * PS) & V.keep) | V.app;
+  }
+  if (check) {  // developer switch (LVA_DBG bit 3): the structural argument above, tested
+    bool bad = false;
+#pragma unroll
+    for (int e = 1; e < LP; e++)
+#pragma unroll
+      for (int e2 = 0; e2 < e; e2++) bad = bad || (mB[e] != NEG && idB[e] == idB[e2] && ptB[e] == ptB[e2]);
+    if (bad) atomicAdd(counters + 2, 1ull);
+  }
+
+  // ---- stage T ----
+  const float wA = lds_f32(V.wrow + 4u * (uint32_t)V.s);
+  uint32_t dropA = 0, dropB = 0;
+#pragma unroll 1
+  for (int a = 0; a < LP; a++) {
+    const uint32_t addr = V.mine + (uint32_t)a * SS;
+    const float mA = lds_f32(addr) + wA;
+    const uint32_t idA = lds_u32(addr + LS), ptA = lds_u32(addr + 2 * LS);
+    float tm = NEG;
+    uint32_t tb = 0;
+#pragma unroll
+    for (int e = 0; e < LP; e++) {
+      const bool eq = ((idA ^ idB[e]) | (ptA ^ ptB[e])) == 0u;
+      tm = eq ? mB[e] : tm;
+      tb = eq ? (1u << e) : tb;
+    }
+    const bool has = tb != 0u && tm != NEG && mA != NEG;
+    tie = tie || (has && mA == tm);
+    if (has) {
+      if (mA > tm) dropB |= tb;
+      else dropA |= 1u << a;
+    }
+  }
+
+  // ---- stage F ----
+  log.clear();
+  uint32_t keepA = ~dropA & FULL, keepB = ~dropB & FULL;
+  uint32_t addrA = V.mine, addrB = V.srcg, jA = 0, dB = 0;
+  float hA = NEG, hB = NEG;
+  auto head_a = [&]() {
+    hA = NEG;
+    if (keepA != 0u) {
+      jA = (uint32_t)__ffs((int)keepA) - 1u;
+      addrA = V.mine + jA * SS;
+      hA = lds_f32(addrA) + wA;
+    }
+  };
+  auto head_b = [&]() {
+    hB = NEG;
+    const int eB = __ffs((int)keepB) - 1;
+    if (keepB != 0u && eB < nB) {
+      dB = (uint32_t)(desc >> (8 * eB)) & 0xffu;
+      const uint32_t crf = dB >> 4;
+      addrB = V.srcg + crf * LS + (dB & 15u) * SS;
+      hB = lds_f32(addrB) + lds_f32(V.wrow + 4u * crf);
+    }
+  };
+  head_a();
+  head_b();
+  int l = 0;
+  float last = __int_as_float(0x7f800000);
+  uint32_t *d = dst;
+  const uint32_t own_list = NL == 8 ? (uint32_t)V.s : 0u;
+#pragma unroll 1
+  while (true) {
+    const float best = fmaxf(hA, hB);
+    if (best == NEG) break;
+    tie = tie || hA == hB;
+    const bool pop_a = hA >= hB;
+    const uint32_t addr = pop_a ? addrA : addrB, ps = pop_a ? LS : PS;
+    const uint32_t id = lds_u32(addr + ps), raw = lds_u32(addr + 2 * ps);
+    const uint32_t pt = pop_a ? raw : ((raw & V.keep) | V.app);
+    __stcs(d, __float_as_uint(best));
+    __stcs(d + GP, id);
+    __stcs(d + 2 * GP, pt);
+    d += 8;
+    log.push(0u, pop_a ? ((own_list << 4) | jA) : (NL == 8 ? dB : (0x10u | (dB & 15u))));
+    l++;
+    last = best;
+    if (pop_a) {
+      keepA &= keepA - 1u;
+      head_a();
+    } else {
+      keepB &= keepB - 1u;
+      head_b();
+    }
+    if (l == LP) break;
+  }
+  tie = tie || (fmaxf(hA, hB) == last);  // the candidate behind the last one kept (l == 0: last = +inf)
+  return tie ? -1 : l;
+}
+
+// Which merge serves this state: rows without history, the two-stage merge, or the pop-by-pop loop.
+template <int LP, int NL>
+__device__ __forceinline__ int merge_state(uint32_t *dst, const ListView<LP, NL> &V, int L, AcceptLog<LP> &log, bool nohist,
+                                           bool two_stage, bool check, unsigned am,
+                                           unsigned long long *counters) {
+  if (nohist) return merge_first_only<LP, NL>(dst, V, log);
+  if constexpr (LP <= 8) {
+    if (two_stage) return merge_two_stage<LP, NL>(dst, V, log, am, check, counters);
+  }
+  if (L == LP) return merge_lists<LP, NL, true>(dst, V, L, log);
+  return merge_lists<LP, NL, false>(dst, V, L, log);
+}
+
 // Boundary rows: publish the interned id of (chain id, partial chunk) of every entry just written.
 // An entry taken over from the state's own list keeps the id that list published one step ago;
 // only entries that moved in are looked up in (or added to) the read's chain table.
@@ -420,6 +608,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
     return;
   }
   const int L = (int)K.L;
+  const unsigned am = __activemask();  // the lanes of this warp that own a valid state (roles are per warp)
+  const bool two_stage = LP <= 8 && L == LP && !R.xdup && !(A.dbg & 4u);  // LVA_DBG bit 2: the pop-by-pop merge of merge_lists() everywhere
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
   const uint32_t *srcg = src + src_g;
@@ -437,16 +627,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   if (role == 0) {
     ListView<LP, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    if (R.nohist) n_acc = merge_first_only<LP, 8>(dst, V, log);
-    else if (L == LP) n_acc = merge_lists<LP, 8, true>(dst, V, L, log);
-    else n_acc = merge_lists<LP, 8, false>(dst, V, L, log);
+    n_acc = merge_state<LP, 8>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters);
     if (R.boundary && n_acc > 0) publish_ids<LP, 8>(V, log, n_acc, nidw, nid_own, tab, A, z);
   } else {
     ListView<LP, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    if (R.nohist) n_acc = merge_first_only<LP, 2>(dst, V, log);
-    else if (L == LP) n_acc = merge_lists<LP, 2, true>(dst, V, L, log);
-    else n_acc = merge_lists<LP, 2, false>(dst, V, L, log);
+    n_acc = merge_state<LP, 2>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters);
     if (R.boundary && n_acc > 0) publish_ids<LP, 2>(V, log, n_acc, nidw, nid_own, tab, A, z);
   }
   if (n_acc < 0) {  // metrics tie where libstdc++'s heap order could show: redo this state exactly

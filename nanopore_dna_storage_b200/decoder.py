@@ -192,7 +192,8 @@ def code_tables(mem_conv: int, rate: int, msg_len: int, rc: bool = False, sync_m
     P = t.nstate_pos
     return dict(G=(t.G[0], t.G[1]), init=t.initial_state, final=t.final_state, punc=list(t.punc[:t.punc_len]),
                 nstate_pos=P, pos2msg=list(t.pos2msg[:P]), valid_mask=list(t.valid_mask[:P]),
-                valid_value=list(t.valid_value[:P]), history_words=list(t.history_words[:P]))
+                valid_value=list(t.valid_value[:P]), history_words=list(t.history_words[:P]),
+                first_run_row=list(t.first_run_row[:P]))
 
 
 def band(t: int, nblk: int, nstate_pos: int, max_deviation: int, unfused: bool = False):

@@ -267,3 +267,42 @@ def test_longest_messages_use_all_history_words(oracle, mem, rate, msg_len, L):
     w = synth.Workload("long", mem, rate, msg_len, L, 20, sub=0.004, dele=0.0085, ins=0.0005, seed=7200 + mem)
     _compare(oracle, w, 2, exact_only=False, tag=f"long m{mem} r{rate}")
     _compare(oracle, w, 1, exact_only=True, tag=f"long exact m{mem} r{rate}")
+
+
+def test_two_stage_merge_precondition_holds(oracle, tmp_path):
+    """lva_fast.cuh merge_two_stage() relies on the move-in candidates of a state being pairwise distinct on
+    every row the host did not mark (code_tables.cpp first_run_rows).  LVA_DBG bit 3 makes the kernel test
+    that claim for every state it merges (the switch is read once per process, hence the subprocess); the
+    same run must still reproduce the oracle, on hard reads (beta 3: lists full of near-equal alternatives),
+    in both orientations and on a code whose first run is long."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from nanopore_dna_storage_b200 import synth
+from nanopore_dna_storage_b200.decoder import ListDecoder
+from oracle import binding as ob
+out = []
+for (mem, rate, msg_len, L, rc) in [(11, 5, 60, 8, False), (11, 5, 60, 8, True), (8, 7, 60, 8, True), (6, 5, 100, 4, False), (8, 2, 100, 2, False)]:
+    w = synth.Workload("t", mem, rate, msg_len, L, 20, sub=0.02, dele=0.02, ins=0.01, seed=7100 + mem + rate, betas=(3.0, 4.0))
+    reads = [synth.make_read(w, i) for i in range(4)]
+    with ListDecoder(mem, rate, msg_len, L, 20, rc=rc) as dec:
+        got = dec.decode([r.post for r in reads])
+        tm = dec.timing()
+    same = True
+    for r, (bits, scores) in zip(reads, got):
+        st, obits, oscores = ob.oracle_decode(r.post, mem, rate, msg_len, L, 20, rc)
+        same = same and st == 0 and bits.shape == obits.shape and np.array_equal(bits, obits) \
+            and np.array_equal(scores.view(np.uint32), oscores.view(np.uint32))
+    out.append(dict(cfg=[mem, rate, msg_len, L, rc], same=bool(same), failures=int(tm["structure_check_failures"])))
+print("RESULT " + json.dumps(out))
+''' % root
+    env = dict(os.environ, LVA_DBG="8")
+    p = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    for rec in json.loads(line[7:]):
+        assert rec["same"], rec
+        assert rec["failures"] == 0, rec

@@ -195,3 +195,54 @@ def test_product_code_never_touches_the_oracle():
             posteriors.transpost_crf_flipflop([np.zeros((3, 40), np.float32)])
         with pytest.raises(RuntimeError):
             trim.find_barcodes_and_orientation(["ACGT" * 30], [list(range(1, 121))], "ACGTACGT", "TTGGCCAA", 6, 40)
+
+
+def _first_run_brute(mem, rate, msg_len, rc, nbits):
+    """Rows a message can reach with all its bases equal, by enumeration: every setting of the nbits message
+    bits the first rows depend on (forward: the first bits; reverse complement: the last ones)."""
+    t = decoder.code_tables(mem, rate, msg_len, rc)
+    P, pos = t["nstate_pos"], t["pos2msg"]
+    if not rc:
+        rows = max(q for q in range(P) if pos[q] <= nbits)          # bases 1..rows read message bits < nbits only
+    else:
+        # rc row q emits the complement of forward base P-q; that base reads forward bits >= pos_fwd[P-q-1] - mem
+        fpos = decoder.code_tables(mem, rate, msg_len, False)["pos2msg"]
+        rows = max(q for q in range(1, P) if fpos[P - q - 1] - mem >= msg_len - nbits)
+    longest = 0
+    lib = _lib.lib()
+    out = np.zeros(2 * (msg_len + mem) + 8, dtype=np.uint8)
+    n_out = C.c_uint32(0)
+    bits = np.zeros(msg_len, dtype=np.uint8)
+    for v in range(1 << nbits):
+        chunk = [(v >> i) & 1 for i in range(nbits)]
+        if rc:
+            bits[msg_len - nbits:] = chunk
+        else:
+            bits[:nbits] = chunk
+        # the library's encoder (checked against the reference's in test_oracle_vs_reference.py)
+        assert lib.lva_encode(mem, rate, bits.ctypes.data, msg_len, out.ctypes.data, out.size, C.byref(n_out)) == 0
+        coded = out[:n_out.value]
+        bases = 2 * coded[0::2] + coded[1::2]
+        if rc:
+            bases = 3 - bases[::-1]
+        run = 1
+        while run < rows and bases[run] == bases[0]:
+            run += 1
+        longest = max(longest, run)
+    return rows, longest, t["first_run_row"]
+
+
+@pytest.mark.parametrize("mem,rate,rc,nbits", [(6, 1, False, 14), (8, 2, False, 14), (8, 5, False, 14), (11, 1, False, 12),
+                                               (11, 5, False, 17), (14, 1, False, 12), (6, 1, True, 16), (6, 3, True, 17),
+                                               (8, 1, True, 17)])
+def test_first_run_rows_match_enumeration(mem, rate, rc, nbits):
+    """code_tables.cpp first_run_rows(): the rows where one message can sit in two crf states (only the
+    parity of a message's FIRST homopolymer run is open, VCC:657-663) -- the two-stage merge of
+    lva_fast.cuh is used on all other rows."""
+    msg_len = 40 if _lib.lib().lva_check_params(mem, rate, 40) == 0 else 41
+    rows, longest, table = _first_run_brute(mem, rate, msg_len, rc, nbits)
+    assert table[0] == 1
+    assert longest < rows, "enumeration window too short to see the end of the longest first run"
+    for q in range(1, rows + 1):
+        assert table[q] == (1 if q <= longest else 0), (q, longest, table[:rows + 1])
+    assert sum(table) == longest + 1   # and no row beyond
