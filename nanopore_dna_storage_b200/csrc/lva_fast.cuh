@@ -276,7 +276,7 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL>
 // Returns the number of accepted entries, or -1 on a tie.
 template <int LP, int NL>
 __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP, NL> &V, AcceptLog<LP> &log, unsigned am,
-                                               bool check, unsigned long long *counters) {
+                                               bool check, unsigned long long *counters, uint64_t *own_bar) {
   static_assert(LP <= 8, "stage T keeps 3*LP words of move-in candidates in registers");
   using View = ListView<LP, NL>;
   constexpr uint32_t SS = View::SS, LS = View::LS, PS = View::PS, GP = 64u * LP;
@@ -346,6 +346,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
   }
 
   // ---- stage T ----
+  mbar_wait(own_bar, 0);  // the own lists were the last copies issued: stage B ran under them
   const float wA = lds_f32(V.wrow + 4u * (uint32_t)V.s);
   uint32_t dropA = 0, dropB = 0;
 #pragma unroll 1
@@ -431,11 +432,12 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
 template <int LP, int NL>
 __device__ __forceinline__ int merge_state(uint32_t *dst, const ListView<LP, NL> &V, int L, AcceptLog<LP> &log, bool nohist,
                                            bool two_stage, bool check, unsigned am,
-                                           unsigned long long *counters) {
-  if (nohist) return merge_first_only<LP, NL>(dst, V, log);
+                                           unsigned long long *counters, uint64_t *own_bar) {
   if constexpr (LP <= 8) {
-    if (two_stage) return merge_two_stage<LP, NL>(dst, V, log, am, check, counters);
+    if (two_stage && !nohist) return merge_two_stage<LP, NL>(dst, V, log, am, check, counters, own_bar);
   }
+  mbar_wait(own_bar, 0);  // every other merge reads the own list from its first instruction on
+  if (nohist) return merge_first_only<LP, NL>(dst, V, log);
   if (L == LP) return merge_lists<LP, NL, true>(dst, V, L, log);
   return merge_lists<LP, NL, false>(dst, V, L, log);
 }
@@ -512,12 +514,16 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   }
   const bool valid = (c & R.vmask) == R.vval && !(one_bit && warp >= 4);
 
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);          // bytes 0..7
+  // three load barriers, in the order the data is needed: [0] posterior block + predecessor tile (every warp, at
+  // once), [1] own lists of the flop warps (right after), [2] own lists of the flip warps (only after their stage B)
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 48);     // bytes 192..215
   float *post = reinterpret_cast<float *>(smem + 4);           // bytes 16..175
   uint32_t *src = smem + 64;                                   // byte 256: [plane][crf][slot][32]
   uint32_t *own = src + 24 * LP * TG;                          // per warp [plane][slot][32] (one-bit rows: 2 pieces per warp)
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    mbar_init(bar + 2, 1);
     fence_barrier_init();
   }
   if (!__syncthreads_or(valid)) return;
@@ -528,7 +534,9 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   if (tid == 0) {
     const uint32_t src_planes = R.post_boundary ? 1u : 3u;
     const uint32_t plane_bytes = 8u * LP * TG * 4u, warp_bytes = 3u * LP * TG * 4u;
-    mbar_expect_tx(bar, 160u + (src_planes + (R.post_boundary ? 1u : 0u)) * plane_bytes + 8u * warp_bytes);
+    mbar_expect_tx(bar, 160u + (src_planes + (R.post_boundary ? 1u : 0u)) * plane_bytes);
+    mbar_expect_tx(bar + 1, 4u * warp_bytes);
+    mbar_expect_tx(bar + 2, 4u * warp_bytes);
     bulk_g2s(post, A.post + (unsigned long long)A.post_blk[z] * 40, 160u, bar);
     const int src_piece = (int)((prv_row0 + wp1) * ppr + tile * 4u);
     for (uint32_t pl = 0; pl < src_planes; pl++)
@@ -537,15 +545,19 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
       tensor3d_g2s(src + 8 * LP * TG, &nid_map, 0,
                    (int)(((z * 2u + (A.t & 1u)) * K.nid_ring + R.src_nid_slot) * ppr + tile * 4u), 0, bar);
     const int own_piece0 = (int)((prv_row0 + wp) * ppr);
-    if (!one_bit) {
-      for (uint32_t w = 0; w < 8; w++)
+    if (!one_bit) {  // flop warps (4..7) first
+      for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t w = i ^ 4u;
         tensor5d_g2s(own + w * 3 * LP * TG, &own_map, 0, (int)(4u * (w >> 2)), 0, 0,
-                     own_piece0 + (int)(((w & 3u) << (K.mem - 5)) + tile), bar);
-    } else {
-      for (uint32_t w = 0; w < 4; w++)
+                     own_piece0 + (int)(((w & 3u) << (K.mem - 5)) + tile), bar + 1 + (i >> 2));
+      }
+    } else {         // flop warps are 2..3
+      for (uint32_t i = 0; i < 4; i++) {
+        const uint32_t w = i ^ 2u;
         for (uint32_t h = 0; h < 2; h++)
           tensor5d_g2s(own + (w * 2 + h) * 3 * LP * TG, &own_map, 0, (int)(4u * (w >> 1)), 0, 0,
-                       own_piece0 + (int)(((w & 1u) << (K.mem - 4)) + tile * 2u + h), bar);
+                       own_piece0 + (int)(((w & 1u) << (K.mem - 4)) + tile * 2u + h), bar + 1 + (i >> 1));
+      }
     }
     if (A.dbg >> 8) {
       // developer switch: pull the lists of the CTA `dist` places later in launch order into L2 now
@@ -594,10 +606,16 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   const uint32_t appv = appended_bits(xy, R.shift, R.app) << R.app_pos;
   const uint32_t keep = R.post_boundary ? 0u : 0xffffffffu;
   mbar_wait(bar, 0);
+  if (A.dbg & 32u) {  // developer switch: every copy awaited before any work (A/B of the barrier split)
+    mbar_wait(bar + 1, 0);
+    mbar_wait(bar + 2, 0);
+  }
   if (!valid) return;
+  uint64_t *own_bar = bar + (role == 0 ? 2 : 1);
 
   uint32_t *mine = own + pos;
   if (A.dbg & 2u) {  // developer switch: data movement only -- the own list is copied to the new list (WRONG results)
+    mbar_wait(own_bar, 0);
     if (A.dbg & 16u) { if (mine[0] == 0x12345678u) dst[0] = src[src_g]; return; }  // ... and no stores
 #pragma unroll
     for (int l = 0; l < LP; l++) {
@@ -627,12 +645,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   if (role == 0) {
     ListView<LP, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    n_acc = merge_state<LP, 8>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters);
+    n_acc = merge_state<LP, 8>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar);
     if (R.boundary && n_acc > 0) publish_ids<LP, 8>(V, log, n_acc, nidw, nid_own, tab, A, z);
   } else {
     ListView<LP, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    n_acc = merge_state<LP, 2>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters);
+    n_acc = merge_state<LP, 2>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar);
     if (R.boundary && n_acc > 0) publish_ids<LP, 2>(V, log, n_acc, nidw, nid_own, tab, A, z);
   }
   if (n_acc < 0) {  // metrics tie where libstdc++'s heap order could show: redo this state exactly
