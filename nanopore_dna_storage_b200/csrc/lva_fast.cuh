@@ -46,11 +46,23 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float
 //                               s-4 of the predecessor conv state (column s-4 of row 4).
 // All list accesses go through 32-bit shared-window addresses computed once per thread (plain
 // generic pointers made the compiler rebuild the shared window base inside the merge loop).
+// The predecessor tile is staged piece by piece as it lies in HBM ([plane][crf][slot][8 conv states], one
+// bulk copy per piece, 8 words of padding between pieces so that the four pieces sit in different banks):
+// a lane's column is (piece, conv state & 7).  The own lists keep rows of 32 words per (plane, slot).
+template <int LP>
+struct TileGeom {
+  static constexpr uint32_t kPieceWords = 3 * 8 * LP * 8;       // = StepArgs::piece_words
+  static constexpr uint32_t kPieceStride = kPieceWords + 8;     // words, staged
+  static constexpr uint32_t kTileWords = 4 * kPieceStride;
+};
+
 template <int LP, int NL>
 struct ListView {
-  static constexpr uint32_t SS = 32 * 4;              // slot stride in bytes
-  static constexpr uint32_t LS = LP * SS;             // between the crf lists of the tile = between the planes of an own list
-  static constexpr uint32_t PS = 8 * LS;              // between the planes of the tile
+  static constexpr uint32_t SS = 32 * 4;              // own list: slot stride in bytes
+  static constexpr uint32_t LS = LP * SS;             // own list: between the planes
+  static constexpr uint32_t TSS = 8 * 4;              // tile: slot stride in bytes
+  static constexpr uint32_t TLS = LP * TSS;           // tile: between the crf lists
+  static constexpr uint32_t TPS = 8 * TLS;            // tile: between the planes
   uint32_t srcg, mine, wrow;  // shared addresses: my predecessor column, my own list, my score row
   uint32_t keep, app;         // identity of a move candidate: (id, (partial & keep) | app)
   int s;
@@ -60,16 +72,16 @@ struct ListView {
   __device__ __forceinline__ void pin() { asm volatile("" : "+r"(srcg), "+r"(mine), "+r"(wrow), "+r"(keep), "+r"(app)); }
   __device__ __forceinline__ int crf_of(int i) const { return NL == 8 ? i : (i == 0 ? s : s - 4); }
   __device__ __forceinline__ bool is_stay(int i) const { return NL == 8 ? i == s : i == 0; }
-  __device__ __forceinline__ uint32_t base(int i) const {
-    return is_stay(i) ? mine : srcg + (uint32_t)crf_of(i) * LS;
+  __device__ __forceinline__ uint32_t entry(int i, int j) const {  // address of the metric of entry j of list i
+    return is_stay(i) ? mine + (uint32_t)j * SS : srcg + (uint32_t)crf_of(i) * TLS + (uint32_t)j * TSS;
   }
   __device__ __forceinline__ float score(int i, int j) const {
-    return lds_f32(base(i) + (uint32_t)j * SS) + lds_f32(wrow + 4u * (uint32_t)crf_of(i));
+    return lds_f32(entry(i, j)) + lds_f32(wrow + 4u * (uint32_t)crf_of(i));
   }
   // (chain id, partial chunk) that entry j of list i would carry at the target
   __device__ __forceinline__ void identity(int i, int j, uint32_t &id, uint32_t &pt) const {
     const bool st = is_stay(i);
-    const uint32_t b = base(i) + (uint32_t)j * SS, ps = st ? LS : PS;
+    const uint32_t b = entry(i, j), ps = st ? LS : TPS;
     id = lds_u32(b + ps);
     const uint32_t raw = lds_u32(b + 2 * ps);
     pt = st ? raw : ((raw & keep) | app);
@@ -279,7 +291,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
                                                bool check, unsigned long long *counters, uint64_t *own_bar) {
   static_assert(LP <= 8, "stage T keeps 3*LP words of move-in candidates in registers");
   using View = ListView<LP, NL>;
-  constexpr uint32_t SS = View::SS, LS = View::LS, PS = View::PS, GP = 64u * LP;
+  constexpr uint32_t SS = View::SS, LS = View::LS, TSS = View::TSS, TLS = View::TLS, TPS = View::TPS, GP = 64u * LP;
   constexpr uint32_t FULL = (1u << LP) - 1u;
   const float NEG = neg_inf();
   bool tie = false;
@@ -290,7 +302,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
   if constexpr (NL == 8) {
     float h[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) h[i] = i == V.s ? NEG : lds_f32(V.srcg + (uint32_t)i * LS) + lds_f32(V.wrow + 4u * (uint32_t)i);
+    for (int i = 0; i < 8; i++) h[i] = i == V.s ? NEG : lds_f32(V.srcg + (uint32_t)i * TLS) + lds_f32(V.wrow + 4u * (uint32_t)i);
     float best, last_m = __int_as_float(0x7f800000);  // +inf: never equals a metric
     int i, last_i = -1;
     select_head<8>(h, best, i);
@@ -309,7 +321,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
       last_i = i;
       float nh = NEG;
       if (live && j + 1 < LP) {
-        nh = lds_f32(V.srcg + (uint32_t)i * LS + (uint32_t)(j + 1) * SS) + lds_f32(V.wrow + 4u * (uint32_t)i);
+        nh = lds_f32(V.srcg + (uint32_t)i * TLS + (uint32_t)(j + 1) * TSS) + lds_f32(V.wrow + 4u * (uint32_t)i);
         ptrs += 1u << (4 * i);
       }
 #pragma unroll
@@ -328,13 +340,13 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
 #pragma unroll
   for (int e = 0; e < LP; e++) {
     const uint32_t d = (uint32_t)(desc >> (8 * e)) & 0xffu, crf = d >> 4;
-    const uint32_t addr = V.srcg + crf * LS + (d & 15u) * SS;
+    const uint32_t addr = V.srcg + crf * TLS + (d & 15u) * TSS;
     const float m = lds_f32(addr) + lds_f32(V.wrow + 4u * crf);
     const bool live = e < nB && m != NEG;
     mB[e] = live ? m : NEG;
     // a dead slot may still hold the identity of an entry that lives elsewhere: it must match nothing
-    idB[e] = live ? lds_u32(addr + PS) : 0xffffffffu;  // no chain id has this value (table slots < 2^27, kRootId)
-    ptB[e] = (lds_u32(addr + 2 * PS) & V.keep) | V.app;
+    idB[e] = live ? lds_u32(addr + TPS) : 0xffffffffu;  // no chain id has this value (table slots < 2^27, kRootId)
+    ptB[e] = (lds_u32(addr + 2 * TPS) & V.keep) | V.app;
   }
   if (check) {  // developer switch (LVA_DBG bit 3): the structural argument above, tested
     bool bad = false;
@@ -389,7 +401,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
     if (keepB != 0u && eB < nB) {
       dB = (uint32_t)(desc >> (8 * eB)) & 0xffu;
       const uint32_t crf = dB >> 4;
-      addrB = V.srcg + crf * LS + (dB & 15u) * SS;
+      addrB = V.srcg + crf * TLS + (dB & 15u) * TSS;
       hB = lds_f32(addrB) + lds_f32(V.wrow + 4u * crf);
     }
   };
@@ -405,7 +417,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
     if (best == NEG) break;
     tie = tie || hA == hB;
     const bool pop_a = hA >= hB;
-    const uint32_t addr = pop_a ? addrA : addrB, ps = pop_a ? LS : PS;
+    const uint32_t addr = pop_a ? addrA : addrB, ps = pop_a ? LS : TPS;
     const uint32_t id = lds_u32(addr + ps), raw = lds_u32(addr + 2 * ps);
     const uint32_t pt = pop_a ? raw : ((raw & V.keep) | V.app);
     __stcs(d, __float_as_uint(best));
@@ -518,8 +530,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   // once), [1] own lists of the flop warps (right after), [2] own lists of the flip warps (only after their stage B)
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 48);     // bytes 192..215
   float *post = reinterpret_cast<float *>(smem + 4);           // bytes 16..175
-  uint32_t *src = smem + 64;                                   // byte 256: [plane][crf][slot][32]
-  uint32_t *own = src + 24 * LP * TG;                          // per warp [plane][slot][32] (one-bit rows: 2 pieces per warp)
+  uint32_t *src = smem + 64;                                   // byte 256: 4 x [plane][crf][slot][8] + padding (TileGeom)
+  uint32_t *own = src + TileGeom<LP>::kTileWords;              // per warp [plane][slot][32] (one-bit rows: 2 pieces per warp)
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init(bar + 1, 1);
@@ -532,18 +544,24 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   const uint32_t prv_row0 = (z * 2u + (A.t & 1u)) * K.window, cur_row0 = (z * 2u + ((A.t + 1u) & 1u)) * K.window;
   // ---- stage ----
   if (tid == 0) {
-    const uint32_t src_planes = R.post_boundary ? 1u : 3u;
-    const uint32_t plane_bytes = 8u * LP * TG * 4u, warp_bytes = 3u * LP * TG * 4u;
-    mbar_expect_tx(bar, 160u + (src_planes + (R.post_boundary ? 1u : 0u)) * plane_bytes);
+    constexpr uint32_t plane_bytes = 8u * LP * 8u * 4u;  // one plane of one piece
+    const uint32_t warp_bytes = 3u * LP * TG * 4u;
+    mbar_expect_tx(bar, 160u + 4u * (R.post_boundary ? 2u : 3u) * plane_bytes);
     mbar_expect_tx(bar + 1, 4u * warp_bytes);
     mbar_expect_tx(bar + 2, 4u * warp_bytes);
     bulk_g2s(post, A.post + (unsigned long long)A.post_blk[z] * 40, 160u, bar);
-    const int src_piece = (int)((prv_row0 + wp1) * ppr + tile * 4u);
-    for (uint32_t pl = 0; pl < src_planes; pl++)
-      tensor3d_g2s(src + pl * 8 * LP * TG, &src_map, 0, src_piece, (int)(pl * 8 * LP), bar);
-    if (R.post_boundary)  // the chain ids of a completed chunk come from the source row's nid plane
-      tensor3d_g2s(src + 8 * LP * TG, &nid_map, 0,
-                   (int)(((z * 2u + (A.t & 1u)) * K.nid_ring + R.src_nid_slot) * ppr + tile * 4u), 0, bar);
+    // the predecessor tile: four consecutive pieces of row p-1, each one contiguous copy (SASS: UBLKCP)
+    const uint32_t *tile_g = A.state + (unsigned long long)(prv_row0 + wp1) * A.row_words + (unsigned long long)tile * 4u * A.piece_words;
+    if (!R.post_boundary) {
+      for (uint32_t q = 0; q < 4; q++)
+        bulk_g2s(src + q * TileGeom<LP>::kPieceStride, tile_g + q * TileGeom<LP>::kPieceWords, 3u * plane_bytes, bar);
+    } else {  // metrics only; the chain ids of a completed chunk come from the source row's nid plane, the partial chunk starts empty
+      const uint32_t *nid_g = A.nid + nid_base(A, K, z, A.t & 1u, R.src_nid_slot) + (unsigned long long)tile * 4u * (64u * LP);
+      for (uint32_t q = 0; q < 4; q++) {
+        bulk_g2s(src + q * TileGeom<LP>::kPieceStride, tile_g + q * TileGeom<LP>::kPieceWords, plane_bytes, bar);
+        bulk_g2s(src + q * TileGeom<LP>::kPieceStride + 64u * LP, nid_g + q * (64u * LP), plane_bytes, bar);
+      }
+    }
     const int own_piece0 = (int)((prv_row0 + wp) * ppr);
     if (!one_bit) {  // flop warps (4..7) first
       for (uint32_t i = 0; i < 8; i++) {
@@ -616,11 +634,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   uint32_t *mine = own + pos;
   if (A.dbg & 2u) {  // developer switch: data movement only -- the own list is copied to the new list (WRONG results)
     mbar_wait(own_bar, 0);
-    if (A.dbg & 16u) { if (mine[0] == 0x12345678u) dst[0] = src[src_g]; return; }  // ... and no stores
+    const uint32_t *col = src + (uint32_t)(src_g >> 3) * TileGeom<LP>::kPieceStride + (uint32_t)(src_g & 7);
+    if (A.dbg & 16u) { if (mine[0] == 0x12345678u) dst[0] = col[0]; return; }  // ... and no stores
 #pragma unroll
     for (int l = 0; l < LP; l++) {
       __stcs(dst + l * 8, mine[l * 32]);
-      __stcs(dst + GP + l * 8, mine[(LP + l) * 32] ^ src[src_g + l * 32]);
+      __stcs(dst + GP + l * 8, mine[(LP + l) * 32] ^ col[l * 8]);
       __stcs(dst + 2 * GP + l * 8, mine[(2 * LP + l) * 32]);
     }
     return;
@@ -630,7 +649,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   const bool two_stage = LP <= 8 && L == LP && !R.xdup && !(A.dbg & 4u);  // LVA_DBG bit 2: the pop-by-pop merge of merge_lists() everywhere
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
-  const uint32_t *srcg = src + src_g;
+  const uint32_t *srcg = src + (uint32_t)(src_g >> 3) * TileGeom<LP>::kPieceStride + (uint32_t)(src_g & 7);
   AcceptLog<LP> log;
   int n_acc;
   uint32_t *nidw = nullptr;
@@ -654,7 +673,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
     if (R.boundary && n_acc > 0) publish_ids<LP, 2>(V, log, n_acc, nidw, nid_own, tab, A, z);
   }
   if (n_acc < 0) {  // metrics tie where libstdc++'s heap order could show: redo this state exactly
-    const int n = exact_merge<LP>(src, mine, post, L, TG, 32, keep, appv, s, src_g);
+    const int n = exact_merge<LP>(src + (uint32_t)(src_g >> 3) * TileGeom<LP>::kPieceStride, mine, post, L, 8, 32, keep, appv, s, src_g & 7);
     atomicAdd(A.counters, 1ull);
     for (int l = 0; l < L; l++) {
       dst[l * 8] = mine[l * 32];
@@ -773,8 +792,8 @@ inline cudaError_t l1_launch_step(cudaStream_t st, const L1Args &a, const CodeSp
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 inline size_t fast_smem_bytes(uint32_t LP) {
-  // predecessor tile + own (stay) lists of every thread: 3 planes each
-  return 256 + (size_t)2 * 3 * 8 * LP * 32 * 4;
+  // predecessor tile (4 pieces + padding) + own (stay) lists of every thread: 3 planes each
+  return 256 + (size_t)4 * (3 * 8 * LP * 8 + 8) * 4 + (size_t)3 * 8 * LP * 32 * 4;
 }
 
 #define LVA_FAST_LP_CASES(X) X(2) X(4) X(8) X(16)
