@@ -7,17 +7,20 @@
 //   * every list entry is 3 words (metric, chain id, partial chunk -- lva_device.cuh), so ONE
 //     kernel serves every row of every code: 6 KB of shared memory per warp, 4 CTAs per SM at
 //     list size 8;
-//   * the predecessor tile (4 octet pieces of row p-1) arrives as one 3-D TMA tensor copy per
-//     plane, re-shaped to rows of 32 conv states; the CTA's own (stay) lists are whole pieces of
-//     row p, one 5-D tensor copy per warp re-shaped to [plane][slot][4 bases x 8 conv states];
-//     the step's 40 transition scores ride the same mbarrier (SASS: UTMALDG / UBLKCP);
-//   * each thread owns one target state (p, c, s); the 32 lanes of a warp read 32 DIFFERENT
-//     predecessor conv states, which are 32 different banks -> no bank conflicts whatever the
-//     (crf, slot, plane) pattern;
-//   * the new list is built by a flat k-way merge (one candidate popped per trip by every lane)
-//     with de-duplication on (chain id, partial chunk): a one-byte signature and a (list, slot)
-//     descriptor per accepted entry are kept in byte shift registers, signature matches are
-//     verified against the staged lists; an accepted entry is stored to the new list right away;
+//   * the predecessor tile (4 octet pieces of row p-1) arrives as four contiguous TMA bulk copies,
+//     piece by piece as it lies in HBM (SASS: UBLKCP); the CTA's own (stay) lists are whole pieces
+//     of row p, one 5-D tensor copy per warp re-shaped to [plane][slot][4 bases x 8 conv states]
+//     (UTMALDG).  Three mbarriers in the order the data is needed: transition scores + tile, own
+//     lists of the flop warps, own lists of the flip warps (which merge their seven predecessor
+//     lists first);
+//   * each thread owns one target state (p, c, s).  Own lists: bank = lane, no conflicts.  Tile:
+//     a lane's column is (piece, conv state & 7), the pieces padded 8 words apart: lanes reading
+//     the same slot never conflict, lanes at different slots may (two-way on average);
+//   * list size == slot count <= 8: merge_two_stage() -- the best move-in candidates by a plain
+//     7-way merge, twins of the own entries found by exact compares in registers, two-way merge
+//     of the survivors; every stage runs a fixed number of trips in lock step.  Other list sizes
+//     and the first rows of the trellis: merge_lists(), a pop-by-pop k-way merge with
+//     de-duplication on (chain id, partial chunk) through one-byte signatures;
 //   * whenever the reference's heap order could show in the output (exactly equal metrics from
 //     different lists) the thread re-runs that state through exact_merge(), which reproduces
 //     libstdc++'s heap order (VCC:762-795).  Without a tie the pop sequence of any correct k-way
@@ -288,7 +291,7 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL>
 // Returns the number of accepted entries, or -1 on a tie.
 template <int LP, int NL>
 __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP, NL> &V, AcceptLog<LP> &log, unsigned am,
-                                               bool check, unsigned long long *counters, uint64_t *own_bar) {
+                                               bool check, unsigned long long *counters, uint64_t *own_bar, bool want_log) {
   static_assert(LP <= 8, "stage T keeps 3*LP words of move-in candidates in registers");
   using View = ListView<LP, NL>;
   constexpr uint32_t SS = View::SS, LS = View::LS, TSS = View::TSS, TLS = View::TLS, TPS = View::TPS, GP = 64u * LP;
@@ -424,7 +427,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
     __stcs(d + GP, id);
     __stcs(d + 2 * GP, pt);
     d += 8;
-    log.push(0u, pop_a ? ((own_list << 4) | jA) : (NL == 8 ? dB : (0x10u | (dB & 15u))));
+    if (want_log) log.push(0u, pop_a ? ((own_list << 4) | jA) : (NL == 8 ? dB : (0x10u | (dB & 15u))));  // boundary rows: publish_ids()
     l++;
     last = best;
     if (pop_a) {
@@ -444,9 +447,9 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
 template <int LP, int NL>
 __device__ __forceinline__ int merge_state(uint32_t *dst, const ListView<LP, NL> &V, int L, AcceptLog<LP> &log, bool nohist,
                                            bool two_stage, bool check, unsigned am,
-                                           unsigned long long *counters, uint64_t *own_bar) {
+                                           unsigned long long *counters, uint64_t *own_bar, bool want_log) {
   if constexpr (LP <= 8) {
-    if (two_stage && !nohist) return merge_two_stage<LP, NL>(dst, V, log, am, check, counters, own_bar);
+    if (two_stage && !nohist) return merge_two_stage<LP, NL>(dst, V, log, am, check, counters, own_bar, want_log);
   }
   mbar_wait(own_bar, 0);  // every other merge reads the own list from its first instruction on
   if (nohist) return merge_first_only<LP, NL>(dst, V, log);
@@ -475,10 +478,6 @@ __device__ __forceinline__ void publish_ids(const ListView<LP, NL> &V, const Acc
       }
       nidw[(n_acc - 1 - e) * 8] = v;
     }
-}
-
-__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 template <int LP>
@@ -577,30 +576,6 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
                        own_piece0 + (int)(((w & 1u) << (K.mem - 4)) + tile * 2u + h), bar + 1 + (i >> 1));
       }
     }
-    if (A.dbg >> 8) {
-      // developer switch: pull the lists of the CTA `dist` places later in launch order into L2 now
-      const uint32_t dist = A.dbg >> 8;
-      uint32_t n = (z * gridDim.y + blockIdx.y) * gridDim.x + tile + dist;
-      const uint32_t t2 = n % gridDim.x, y2 = (n / gridDim.x) % gridDim.y, z2 = n / (gridDim.x * gridDim.y);
-      if (z2 < gridDim.z) {
-        const uint32_t a2 = A.band_a[z2], p2 = a2 + y2;
-        uint32_t b2 = a2 + A.dev2;
-        if (b2 > K.nrows) b2 = K.nrows;
-        if (p2 > 0 && p2 < b2) {
-          uint32_t w2 = A.band_slot[z2] + y2;
-          if (w2 >= K.window) w2 -= K.window;
-          const uint32_t w21 = w2 == 0 ? K.window - 1 : w2 - 1;
-          const uint32_t *base2 = A.state + ((unsigned long long)z2 * 2 + (A.t & 1u)) * A.parity_words;
-          prefetch_l2(base2 + (unsigned long long)w21 * A.row_words + (unsigned long long)t2 * 4u * A.piece_words, 4u * A.piece_words * 4u);
-          const uint32_t *row2 = base2 + (unsigned long long)w2 * A.row_words;
-          if (K.row[p2].shift != 1) {
-            for (uint32_t r = 0; r < 4; r++) prefetch_l2(row2 + (unsigned long long)((r << (K.mem - 5)) + t2) * A.piece_words, A.piece_words * 4u);
-          } else {
-            for (uint32_t r = 0; r < 2; r++) prefetch_l2(row2 + (unsigned long long)((r << (K.mem - 4)) + t2 * 2u) * A.piece_words, 2u * A.piece_words * 4u);
-          }
-        }
-      }
-    }
   }
   // ---- the rest of the geometry, while the copies fly: my crf state and predecessor column ----
   int s, src_g, pos;
@@ -664,12 +639,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   if (role == 0) {
     ListView<LP, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    n_acc = merge_state<LP, 8>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar);
+    n_acc = merge_state<LP, 8>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar, R.boundary != 0);
     if (R.boundary && n_acc > 0) publish_ids<LP, 8>(V, log, n_acc, nidw, nid_own, tab, A, z);
   } else {
     ListView<LP, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
     V.pin();
-    n_acc = merge_state<LP, 2>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar);
+    n_acc = merge_state<LP, 2>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar, R.boundary != 0);
     if (R.boundary && n_acc > 0) publish_ids<LP, 2>(V, log, n_acc, nidw, nid_own, tab, A, z);
   }
   if (n_acc < 0) {  // metrics tie where libstdc++'s heap order could show: redo this state exactly
