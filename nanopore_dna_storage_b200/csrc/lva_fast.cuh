@@ -531,7 +531,10 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   float *post = reinterpret_cast<float *>(smem + 4);           // bytes 16..175
   uint32_t *src = smem + 64;                                   // byte 256: 4 x [plane][crf][slot][8] + padding (TileGeom)
   uint32_t *own = src + TileGeom<LP>::kTileWords;              // per warp [plane][slot][32] (one-bit rows: 2 pieces per warp)
-  if (tid == 0) {
+  // The copies are issued by lane 0 of the LAST warp: a flop warp (it has some 600 instructions of slack against
+  // the flip warps, the critical path of the CTA), or on one-bit rows of a 256-thread launch a warp with nothing else to do
+  const bool issuer = tid == (int)blockDim.x - 32;
+  if (issuer) {
     mbar_init(bar, 1);
     mbar_init(bar + 1, 1);
     mbar_init(bar + 2, 1);
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   const uint32_t ppr = K.nconv >> 3;  // pieces per row
   const uint32_t prv_row0 = (z * 2u + (A.t & 1u)) * K.window, cur_row0 = (z * 2u + ((A.t + 1u) & 1u)) * K.window;
   // ---- stage ----
-  if (tid == 0) {
+  if (issuer) {
     constexpr uint32_t plane_bytes = 8u * LP * 8u * 4u;  // one plane of one piece
     const uint32_t warp_bytes = 3u * LP * TG * 4u;
     mbar_expect_tx(bar, 160u + 4u * (R.post_boundary ? 2u : 3u) * plane_bytes);
