@@ -18,6 +18,7 @@
 #include "code_tables.hpp"
 #include "lva_kernels.cuh"
 #include "lva_fast.cuh"
+#include "lva_wide.cuh"
 
 using namespace lva;
 
@@ -95,6 +96,7 @@ struct lva_handle {
   int gen_tg = 32;           // tile width of the generic kernel
   size_t gen_smem = 0;
   bool use_fast = false;
+  bool use_wide = false;     // list sizes 17..64: lva_step_wide (lva_wide.cuh)
   bool all_one_bit = false;
   bool fused_band = true;    // VCC:677-679 as a fused multiply-subtract (LVA_FLAG_UNFUSED_BAND clears it)
 };
@@ -400,6 +402,8 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   if (!h->gen_tg) { lva_destroy(h); return fail(LVA_ERR_LIST_SIZE, "list_size too large for shared memory"); }
   if ((e = generic_prepare(h)) != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(generic)", e);
   h->use_fast = !(params->flags & LVA_FLAG_EXACT_ONLY) && (h->survivor || fast_supported(h->LP));
+  h->use_wide = !(params->flags & LVA_FLAG_EXACT_ONLY) && !h->survivor && wide_supported(h->LP);
+  if (h->use_wide && (e = wide_prepare(h->LP)) != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(wide)", e);
   if (h->use_fast && !h->survivor && (e = fast_prepare(h->LP)) != cudaSuccess)
     return cuda_fail("cudaFuncSetAttribute(fast)", e);
 
@@ -695,6 +699,9 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *start
       } else if (h->use_fast) {
         cudaError_t e = fast_launch_step(h->LP, h->stream, a, k, span, active, h->maps, h->all_one_bit);
         if (e != cudaSuccess) { h->err = std::string("fast step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
+      } else if (h->use_wide) {
+        cudaError_t e = wide_launch_step(h->LP, h->stream, a, k, span, active, h->all_one_bit);
+        if (e != cudaSuccess) { h->err = std::string("wide step launch: ") + cudaGetErrorString(e); return LVA_ERR_CUDA; }
       } else {
         dim3 grid(k.nconv / h->gen_tg, span, active);
         cudaError_t e = generic_launch(h, grid, a);

@@ -196,6 +196,7 @@ __device__ __forceinline__ Target locate_target_q(const CodeDev &K, const RowDev
 template <int LP>
 struct MergeLists {
   const uint32_t *src;   // staged tile base + src_g
+  const uint32_t *sid;   // its chain-id plane (src + 8*LP*tg unless the caller keeps the ids elsewhere)
   int tg;                // words between slots of a staged list
   int s;
   uint32_t keep, app;    // identity of a move candidate: (id, (partial & keep) | app)
@@ -209,7 +210,7 @@ struct MergeLists {
       id = st_id[j];
       pt = st_pt[j];
     } else {
-      id = src[((8 + k) * LP + j) * tg];
+      id = sid[(k * LP + j) * tg];
       pt = (src[((16 + k) * LP + j) * tg] & keep) | app;
     }
   }
@@ -217,10 +218,11 @@ struct MergeLists {
 
 template <int LP>
 __device__ __noinline__ int exact_merge(const uint32_t *src, uint32_t *mine, const float *post, int L, int TGv, int NT,
-                                        uint32_t keep, uint32_t app, int s, int src_g) {
+                                        uint32_t keep, uint32_t app, int s, int src_g, const uint32_t *src_id = nullptr) {
   const float NEG = neg_inf();
   MergeLists<LP> M;
   M.src = src + src_g;
+  M.sid = src_id ? src_id + src_g : src + src_g + 8 * LP * TGv;
   M.tg = TGv;
   M.s = s;
   M.keep = keep;
