@@ -14,7 +14,7 @@
 // detection, exact_merge() as the fallback) with one change: the accept log keeps one-byte signatures only, and a
 // signature match is verified against the entry it points at in the NEW list, which the thread itself has just
 // written (program order; plain loads, mostly L1 hits).  Measured on the paper's m = 8, L = 64 configuration:
-// 7.1 reads/s against 1.6 through lva_step_generic; the verification of true duplicates (about every third pop
+// 7.6 reads/s against 1.6 through lva_step_generic (64 registers, 4 CTAs per SM); the verification of true duplicates (about every third pop
 // at this list size, two lanes of a warp at a time) is what the launch waits for (profiles/README.md).  A 32-bit
 // hash screen in shared memory in front of the verification was measured and dropped (4.8 reads/s).
 #pragma once
@@ -168,7 +168,7 @@ __device__ __forceinline__ int merge_wide(uint32_t *dst, const WideView<LP, NL> 
 }
 
 template <int LP>
-__global__ void __launch_bounds__(kWideThreads, 3) lva_step_wide(const StepArgs A) {
+__global__ void __launch_bounds__(kWideThreads, 4) lva_step_wide(const StepArgs A) {
   constexpr uint32_t GP = 64u * LP;
   extern __shared__ __align__(16) uint32_t wsm[];
   float *post = reinterpret_cast<float *>(wsm);               // 40 transition scores (64 words reserved)
