@@ -197,11 +197,10 @@ typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// Tensor maps of lva_step_fast (lva_fast.cuh): the state buffer seen as
-//   src: (8 conv columns | pieces, piece_bytes apart | 24*LP rows of 32 bytes), box {8, 4 pieces, 8*LP rows = one plane}
+// Tensor map of lva_step_fast (lva_fast.cuh) for the own (stay) lists: the state buffer seen as
 //   own: (8 columns | 8 crf lists | LP slots | 3 planes | pieces), box {8, 4 crf, LP, 3, 1 piece}
-// and the nid ring like src with one plane per piece.  cuTensorMapEncodeTiled comes from the
-// driver through the runtime's entry-point query (no link against libcuda).
+// (the predecessor tile and the nid planes are whole pieces: plain bulk copies, no map).
+// cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query (no link against libcuda).
 std::string make_maps(lva_handle *h) {
   void *fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -210,9 +209,8 @@ std::string make_maps(lva_handle *h) {
     return "cuTensorMapEncodeTiled entry point not available";
   const cuuint64_t ppr = h->code.nconv / 8;
   const cuuint64_t pieces = (cuuint64_t)h->n_slots * 2ull * h->window * ppr;
-  const cuuint64_t nid_pieces = (cuuint64_t)h->n_slots * 2ull * h->nid_ring * ppr;
   const cuuint64_t piece_bytes = (cuuint64_t)h->piece_words * 4ull, LP = h->LP;
-  if (pieces > 0x7fffffffull || nid_pieces > 0x7fffffffull) return "state buffer too large for 32-bit tensor coordinates";
+  if (pieces > 0x7fffffffull) return "state buffer too large for 32-bit tensor coordinates";
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   auto enc = [&](CUtensorMap *m, cuuint32_t rank, void *base, const cuuint64_t *dims, const cuuint64_t *strides,
                  const cuuint32_t *box) {
@@ -221,22 +219,10 @@ std::string make_maps(lva_handle *h) {
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
   {
-    const cuuint64_t dims[3] = {8, pieces, 24 * LP}, strides[2] = {piece_bytes, 32};
-    const cuuint32_t box[3] = {8, 4, (cuuint32_t)(8 * LP)};
-    CUresult r = enc(&h->maps.src, 3, h->d_state.p, dims, strides, box);
-    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled(src) failed: " + std::to_string((int)r);
-  }
-  {
     const cuuint64_t dims[5] = {8, 8, LP, 3, pieces}, strides[4] = {LP * 32, 32, 8 * LP * 32, piece_bytes};
     const cuuint32_t box[5] = {8, 4, (cuuint32_t)LP, 3, 1};
     CUresult r = enc(&h->maps.own, 5, h->d_state.p, dims, strides, box);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled(own) failed: " + std::to_string((int)r);
-  }
-  {
-    const cuuint64_t dims[3] = {8, nid_pieces, 8 * LP}, strides[2] = {8 * LP * 32, 32};
-    const cuuint32_t box[3] = {8, 4, (cuuint32_t)(8 * LP)};
-    CUresult r = enc(&h->maps.nid, 3, h->d_nid.p, dims, strides, box);
-    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled(nid) failed: " + std::to_string((int)r);
   }
   return "";
 }

@@ -481,9 +481,7 @@ __device__ __forceinline__ void publish_ids(const ListView<LP, NL> &V, const Acc
 }
 
 template <int LP>
-__global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs A, const __grid_constant__ CUtensorMap src_map,
-                                                              const __grid_constant__ CUtensorMap own_map,
-                                                              const __grid_constant__ CUtensorMap nid_map) {
+__global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs A, const __grid_constant__ CUtensorMap own_map) {
   constexpr int TG = 32;
   constexpr uint32_t GP = 64u * LP;
   extern __shared__ __align__(128) uint32_t smem[];
@@ -788,7 +786,7 @@ inline cudaError_t fast_prepare(uint32_t LP) {
 }
 
 struct FastMaps {
-  CUtensorMap src, own, nid;
+  CUtensorMap own;
 };
 
 // One time step of every read in flight: one launch.
@@ -800,7 +798,7 @@ inline cudaError_t fast_launch_step(uint32_t LP, cudaStream_t st, const StepArgs
   const uint32_t threads = all_one_bit ? 128 : kFastThreads;
   cudaError_t e = cudaErrorInvalidValue;
 #define X(lp) \
-  if (LP == lp) { lva_step_fast<lp><<<grid, threads, fast_smem_bytes(lp), st>>>(a, maps.src, maps.own, maps.nid); e = cudaGetLastError(); }
+  if (LP == lp) { lva_step_fast<lp><<<grid, threads, fast_smem_bytes(lp), st>>>(a, maps.own); e = cudaGetLastError(); }
   LVA_FAST_LP_CASES(X)
 #undef X
   return e;

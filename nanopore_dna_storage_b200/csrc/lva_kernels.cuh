@@ -54,13 +54,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
 }
 // Tiled copies global -> shared through the TMA unit (SASS: UTMALDG), completion on an mbarrier.
 // `map` must live in kernel-parameter space (const __grid_constant__ CUtensorMap).
-__device__ __forceinline__ void tensor3d_g2s(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
-}
 __device__ __forceinline__ void tensor5d_g2s(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4,
                                              uint64_t *bar) {
   asm volatile(
