@@ -389,8 +389,8 @@ lva_handle *lva_create(const lva_params *params, int *status, char *err, size_t 
   if ((e = generic_prepare(h)) != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(generic)", e);
   h->use_fast = !(params->flags & LVA_FLAG_EXACT_ONLY) && (h->survivor || fast_supported(h->LP));
   h->use_wide = !(params->flags & LVA_FLAG_EXACT_ONLY) && !h->survivor && wide_supported(h->LP);
-  if (const char *wv = getenv("LVA_WIDE16"))  // developer A/B: list size 9..16 through lva_step_wide<16>
-    if (atoi(wv) && !(params->flags & LVA_FLAG_EXACT_ONLY) && h->LP == 16) { h->use_wide = true; h->use_fast = false; }
+  if (const char *wv = getenv("LVA_WIDE"))  // developer A/B: list sizes 5..16 through lva_step_wide<8|16>
+    if (atoi(wv) && !(params->flags & LVA_FLAG_EXACT_ONLY) && !h->survivor && (h->LP == 8 || h->LP == 16)) { h->use_wide = true; h->use_fast = false; }
   if (h->use_wide && (e = wide_prepare(h->LP)) != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(wide)", e);
   if (h->use_fast && !h->survivor && (e = fast_prepare(h->LP)) != cudaSuccess)
     return cuda_fail("cudaFuncSetAttribute(fast)", e);

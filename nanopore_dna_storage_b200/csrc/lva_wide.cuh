@@ -280,9 +280,10 @@ __global__ void __launch_bounds__(kWideThreads, 4) lva_step_wide(const StepArgs 
 }
 
 inline bool wide_supported(uint32_t LP) { return LP == 32 || LP == 64; }
-inline bool wide_possible(uint32_t LP) { return LP == 16 || wide_supported(LP); }  // 16: developer A/B against lva_step_fast<16>
+inline bool wide_possible(uint32_t LP) { return LP == 8 || LP == 16 || wide_supported(LP); }  // 8, 16: developer A/B against lva_step_fast
 inline size_t wide_smem_bytes(uint32_t LP) { return (64 + (size_t)(kWideThreads / 32) * 3 * LP) * 4; }
 inline cudaError_t wide_prepare(uint32_t LP) {
+  if (LP == 8) return cudaFuncSetAttribute(lva_step_wide<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(8));
   if (LP == 16) return cudaFuncSetAttribute(lva_step_wide<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(16));
   if (LP == 32) return cudaFuncSetAttribute(lva_step_wide<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(32));
   if (LP == 64) return cudaFuncSetAttribute(lva_step_wide<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(64));
@@ -293,7 +294,8 @@ inline cudaError_t wide_launch_step(uint32_t LP, cudaStream_t st, const StepArgs
                                     bool all_one_bit) {
   dim3 grid(k.nconv / 32, span, active);
   const uint32_t threads = all_one_bit ? 128 : kWideThreads;
-  if (LP == 16) lva_step_wide<16><<<grid, threads, wide_smem_bytes(16), st>>>(a);
+  if (LP == 8) lva_step_wide<8><<<grid, threads, wide_smem_bytes(8), st>>>(a);
+  else if (LP == 16) lva_step_wide<16><<<grid, threads, wide_smem_bytes(16), st>>>(a);
   else if (LP == 32) lva_step_wide<32><<<grid, threads, wide_smem_bytes(32), st>>>(a);
   else if (LP == 64) lva_step_wide<64><<<grid, threads, wide_smem_bytes(64), st>>>(a);
   else return cudaErrorInvalidValue;
