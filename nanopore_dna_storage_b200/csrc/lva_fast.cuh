@@ -16,7 +16,7 @@
 //   * each thread owns one target state (p, c, s).  Own lists: bank = lane, no conflicts.  Tile:
 //     a lane's column is (piece, conv state & 7), the pieces padded 8 words apart: lanes reading
 //     the same slot never conflict, lanes at different slots may (two-way on average);
-//   * list size == slot count <= 8: merge_two_stage() -- the best move-in candidates by a plain
+//   * list size == slot count <= 16: merge_two_stage() -- the best move-in candidates by a plain
 //     7-way merge, twins of the own entries found by exact compares in registers, two-way merge
 //     of the survivors; every stage runs a fixed number of trips in lock step.  Other list sizes
 //     and the first rows of the trellis: merge_lists(), a pop-by-pop k-way merge with
@@ -267,7 +267,32 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL>
   return tie ? -1 : l;
 }
 
-// Two-stage merge (list size == slot count <= 8; every row whose source row cannot hold one message in
+// LP one-byte descriptors (tile crf << 4 | slot), entry e at byte e: one 64-bit word up to 8 slots, two for 16.
+template <int LP>
+struct DescVec {
+  static constexpr int NW = LP <= 8 ? 1 : 2;
+  unsigned long long w[NW];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = 0;
+  }
+  // shift every entry one place down and put d in the last place: after LP pushes the first push sits at entry 0
+  __device__ __forceinline__ void push_back(uint32_t d) {
+    if (NW == 2) w[0] = (w[0] >> 8) | (w[NW - 1] << 56);
+    constexpr int top = LP <= 8 ? 8 * LP - 8 : 56;
+    w[NW - 1] = (w[NW - 1] >> 8) | ((unsigned long long)d << top);
+  }
+  __device__ __forceinline__ void shift_down(int places) {  // 0 <= places <= LP
+#pragma unroll 1
+    for (int i = 0; i < places; i++) push_back(0u);
+  }
+  __device__ __forceinline__ uint32_t get(int e) const {
+    const unsigned long long v = (NW == 2 && e >= 8) ? w[NW - 1] : w[0];
+    return (uint32_t)(v >> (8 * (e & 7))) & 0xffu;
+  }
+};
+
+// Two-stage merge (list size == slot count <= 16; every row whose source row cannot hold one message in
 // two crf lists -- RowDev::xdup, code_tables.cpp first_run_rows()).
 //
 // A message reaches a state at most twice per step: through the state's own (stay) list A and through
@@ -292,13 +317,14 @@ __device__ __forceinline__ int merge_lists(uint32_t *dst, const ListView<LP, NL>
 template <int LP, int NL>
 __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP, NL> &V, AcceptLog<LP> &log, unsigned am,
                                                bool check, unsigned long long *counters, uint64_t *own_bar, bool want_log) {
-  static_assert(LP <= 8, "stage T keeps 3*LP words of move-in candidates in registers");
+  static_assert(LP <= 16, "stage T keeps 3*LP words of move-in candidates in registers (16 slots: 2 CTAs per SM by shared memory anyway)");
   using View = ListView<LP, NL>;
   constexpr uint32_t SS = View::SS, LS = View::LS, TSS = View::TSS, TLS = View::TLS, TPS = View::TPS, GP = 64u * LP;
   constexpr uint32_t FULL = (1u << LP) - 1u;
   const float NEG = neg_inf();
   bool tie = false;
-  unsigned long long desc = 0;  // byte e = (tile crf << 4 | slot) of the e-th best move-in candidate
+  DescVec<LP> desc;  // entry e = (tile crf << 4 | slot) of the e-th best move-in candidate
+  desc.clear();
   int nB = LP;                  // live move-in candidates among them
 
   // ---- stage B ----
@@ -317,7 +343,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
       const bool live = best != NEG;
       if (!__any_sync(am, live)) break;
       const int j = (ptrs >> (4 * i)) & 15;
-      desc = (desc >> 8) | ((unsigned long long)(uint32_t)((i << 4) | j) << (8 * LP - 8));
+      desc.push_back((uint32_t)((i << 4) | j));
       nB += live ? 1 : 0;
       tie = tie || (live && best == last_m && i != last_i);
       last_m = best;
@@ -331,10 +357,12 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
       for (int i2 = 0; i2 < 8; i2++) h[i2] = (i2 == i) ? nh : h[i2];
       select_head<8>(h, best, i);
     }
-    desc >>= 8 * (LP - e);
+    desc.shift_down(LP - e);
     tie = tie || (best != NEG && best == last_m);  // the candidate behind the LP-th: which of the two is in B?
   } else {
-    desc = (0x0706050403020100ull | (0x1010101010101010ull * (unsigned long long)(uint32_t)(V.s - 4))) & (~0ull >> (64 - 8 * LP));
+    const unsigned long long crfs = 0x1010101010101010ull * (unsigned long long)(uint32_t)(V.s - 4);
+    desc.w[0] = (0x0706050403020100ull | crfs) & (~0ull >> (LP >= 8 ? 0 : 64 - 8 * LP));
+    if (DescVec<LP>::NW == 2) desc.w[DescVec<LP>::NW - 1] = 0x0f0e0d0c0b0a0908ull | crfs;
   }
 
   // ---- the move-in candidates, into registers ----
@@ -342,7 +370,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
   uint32_t idB[LP], ptB[LP];
 #pragma unroll
   for (int e = 0; e < LP; e++) {
-    const uint32_t d = (uint32_t)(desc >> (8 * e)) & 0xffu, crf = d >> 4;
+    const uint32_t d = desc.get(e), crf = d >> 4;
     const uint32_t addr = V.srcg + crf * TLS + (d & 15u) * TSS;
     const float m = lds_f32(addr) + lds_f32(V.wrow + 4u * crf);
     const bool live = e < nB && m != NEG;
@@ -402,7 +430,7 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
     hB = NEG;
     const int eB = __ffs((int)keepB) - 1;
     if (keepB != 0u && eB < nB) {
-      dB = (uint32_t)(desc >> (8 * eB)) & 0xffu;
+      dB = desc.get(eB);
       const uint32_t crf = dB >> 4;
       addrB = V.srcg + crf * TLS + (dB & 15u) * TSS;
       hB = lds_f32(addrB) + lds_f32(V.wrow + 4u * crf);
@@ -448,7 +476,7 @@ template <int LP, int NL>
 __device__ __forceinline__ int merge_state(uint32_t *dst, const ListView<LP, NL> &V, int L, AcceptLog<LP> &log, bool nohist,
                                            bool two_stage, bool check, unsigned am,
                                            unsigned long long *counters, uint64_t *own_bar, bool want_log) {
-  if constexpr (LP <= 8) {
+  if constexpr (LP <= 16) {
     if (two_stage && !nohist) return merge_two_stage<LP, NL>(dst, V, log, am, check, counters, own_bar, want_log);
   }
   mbar_wait(own_bar, 0);  // every other merge reads the own list from its first instruction on
@@ -481,7 +509,7 @@ __device__ __forceinline__ void publish_ids(const ListView<LP, NL> &V, const Acc
 }
 
 template <int LP>
-__global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs A, const __grid_constant__ CUtensorMap own_map) {
+__global__ void __launch_bounds__(kFastThreads, LP <= 8 ? 4 : 2) lva_step_fast(const StepArgs A, const __grid_constant__ CUtensorMap own_map) {
   constexpr int TG = 32;
   constexpr uint32_t GP = 64u * LP;
   extern __shared__ __align__(128) uint32_t smem[];
@@ -622,7 +650,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) lva_step_fast(const StepArgs 
   }
   const int L = (int)K.L;
   const unsigned am = __activemask();  // the lanes of this warp that own a valid state (roles are per warp)
-  const bool two_stage = LP <= 8 && L == LP && !R.xdup && !(A.dbg & 4u);  // LVA_DBG bit 2: the pop-by-pop merge of merge_lists() everywhere
+  const bool two_stage = LP <= 16 && L == LP && !R.xdup && !(A.dbg & 4u);  // LVA_DBG bit 2: the pop-by-pop merge of merge_lists() everywhere
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
   const uint32_t *srcg = src + (uint32_t)(src_g >> 3) * TileGeom<LP>::kPieceStride + (uint32_t)(src_g & 7);
