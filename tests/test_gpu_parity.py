@@ -285,7 +285,7 @@ from nanopore_dna_storage_b200 import synth
 from nanopore_dna_storage_b200.decoder import ListDecoder
 from oracle import binding as ob
 out = []
-for (mem, rate, msg_len, L, rc) in [(11, 5, 60, 8, False), (11, 5, 60, 8, True), (8, 7, 60, 8, True), (6, 5, 100, 4, False), (8, 2, 100, 2, False)]:
+for (mem, rate, msg_len, L, rc) in [(11, 5, 60, 8, False), (11, 5, 60, 8, True), (8, 7, 60, 8, True), (6, 5, 100, 4, False), (8, 2, 100, 2, False), (8, 5, 60, 16, True)]:
     w = synth.Workload("t", mem, rate, msg_len, L, 20, sub=0.02, dele=0.02, ins=0.01, seed=7100 + mem + rate, betas=(3.0, 4.0))
     reads = [synth.make_read(w, i) for i in range(4)]
     with ListDecoder(mem, rate, msg_len, L, 20, rc=rc) as dec:
