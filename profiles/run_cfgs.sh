@@ -1,6 +1,6 @@
 #!/bin/bash
 # the other BASELINE.json configs on one B200 (bench.py, no live CPU sample): one JSON line each
-for wl in C1 C3 C4r2 C4r7 C5; do
+for wl in C1 C3 C4r2 C4r7 C5 C4r2L64; do
   echo "== $wl"
   timeout 600 python bench.py --workload $wl --steps 2 --warmup 1 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import sys,json
