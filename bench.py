@@ -365,7 +365,7 @@ def main():
         value = n_total / wall
         peak, sm_max_mhz, peak_src = measured_peaks()
         achieved = step_bytes * args.steps / (kernel_ms * 1e-3) / 1e9  # per GPU: bytes of one rank / its kernel time
-        tr = committed_json("traffic.json")
+        tr = committed_json("traffic.json") if args.workload == "C2" else None  # the committed capture is a C2 launch
         step_launches = int(dev_acc["step_launches"])
         cand_acs_per_s = step_acs * w.list_size * args.steps / (kernel_ms * 1e-3)  # one GPU, kernel time
         alu_peak = ISSUE_PEAK_THREAD_INSTR * sm_max_mhz * 1e6 / 2.0  # 2 thread-instructions per candidate-ACS
@@ -395,7 +395,8 @@ def main():
                          "hbm_busy_frac": (achieved / peak) * (tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_same_launch"]) if tr else None,
                          "hbm_busy_note": "frac x (measured DRAM traffic / algorithmic bytes of the committed capture): how busy the "
                                           "launch keeps HBM; the gap to frac is re-read and partial-write traffic, not useful work",
-                         "kernel": "lva_step_fast<LP> (every trellis step launch)",
+                         "kernel": ("lva_step_l1" if w.list_size == 1 else "lva_step_fast<LP>" if w.list_size <= 16 else "lva_step_wide<LP>") +
+                                   " (every trellis step launch)",
                          "algorithmic_bytes_per_step": step_bytes,
                          "avg_launch_us": 1e3 * kernel_ms / max(step_launches, 1),
                          "traffic": tr.get("dram_bytes_per_launch") if tr else None,
