@@ -642,6 +642,7 @@ static int decode_core(lva_handle *h, const float *d_post, const uint64_t *start
     a.tab_mask = h->tab_slots - 1;
     a.dev2 = dev2;
     a.code_slot = h->code_slot;
+    a.one = 1u;
     { static const char *dbg_env = getenv("LVA_DBG"); a.dbg = dbg_env ? (uint32_t)atoi(dbg_env) : 0u; }
     ClearArgs clr{};
     clr.state = a.state;

@@ -85,6 +85,7 @@ struct StepArgs {
   uint32_t row_words, piece_words;
   uint32_t tab_mask;              // tab_slots - 1
   uint32_t t, dev2, code_slot;
+  uint32_t one;                   // = 1, a value the compiler cannot see: cond_move() multiplies by it to turn a select into a predicated integer multiply-add (FMA pipe)
   uint32_t dbg;                   // developer switches (LVA_DBG), 0 in production: bit 1 data movement only, bit 2 pop-by-pop merge on every row, bit 3 check the two-stage merge's structural claim, bit 4 no stores, bit 5 wait for every copy before any work
   uint32_t post_blk[kMaxSlots];   // per active slot: index of the posterior block of this step
   uint16_t band_a[kMaxSlots];     // per active slot: first in-band row of this step (VCC:677-678)

@@ -40,6 +40,33 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float(lds_u32(addr)); }
 
+// Conditional moves on the FMA pipe.  The merges are made of compares and selects, all of them ALU-pipe
+// instructions (ncu: ALU pipe 70 % busy, FMA pipe 15 %); `x = p ? y : x` written as a predicated integer
+// multiply-add `@p x = one * y + 0` is the same move issued on the other pipe.  `one` is a 1 the compiler
+// cannot see through: a word of shared memory (kOneWord, written from StepArgs::one) read with a volatile
+// load inside the loop that uses it -- a multiplier known to be loop-invariant lets ptxas hoist the products
+// and turn the moves back into selects.  An integer multiply by 1 is exact for any 32-bit pattern, metrics
+// included.  (profiles/r02c_pmov_ab.log: the four rewrites of this kind together, 51.0 -> 54.3 reads/s on C2.)
+constexpr uint32_t kOneWord = 56;  // word of the CTA's shared memory that holds 1 (bytes 224..227: between the barriers and the tile)
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// (a0 == b0 && a1 == b1) ? (x0 = y0, x1 = y1) : nothing
+__device__ __forceinline__ void cond_move2_if_pair_eq(uint32_t &x0, uint32_t &x1, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1,
+                                                      uint32_t y0, uint32_t y1, uint32_t one) {
+  asm("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %2, %3;\n\tsetp.eq.and.u32 q, %4, %5, q;\n\t"
+      "@q mad.lo.u32 %0, %8, %6, 0;\n\t@q mad.lo.u32 %1, %8, %7, 0;\n\t}"
+      : "+r"(x0), "+r"(x1)
+      : "r"(a0), "r"(b0), "r"(a1), "r"(b1), "r"(y0), "r"(y1), "r"(one));
+}
+
+// (a == b) ? x = y + w : nothing -- a predicated FADD (FMA pipe) in place of an FADD and a select
+__device__ __forceinline__ void cond_add_if_eq(float &x, int a, int b, float y, float w) {
+  asm("{\n\t.reg .pred q;\n\tsetp.eq.s32 q, %1, %2;\n\t@q add.f32 %0, %3, %4;\n\t}" : "+f"(x) : "r"(a), "r"(b), "f"(y), "f"(w));
+}
+
 // Everything a thread needs to address the lists it merges.  Staged lists share one shape:
 // rows of 32 words per (plane, crf, slot); the predecessor tile is [plane][crf][slot], the
 // warp's own lists [plane][slot].
@@ -69,6 +96,7 @@ struct ListView {
   uint32_t srcg, mine, wrow;  // shared addresses: my predecessor column, my own list, my score row
   uint32_t keep, app;         // identity of a move candidate: (id, (partial & keep) | app)
   int s;
+  uint32_t one_addr;          // shared address of kOneWord (cond_move*)
 
   // keep the addresses in registers: left alone, the compiler rebuilds them from the thread's
   // geometry inside the merge loop
@@ -282,10 +310,6 @@ struct DescVec {
     constexpr int top = LP <= 8 ? 8 * LP - 8 : 56;
     w[NW - 1] = (w[NW - 1] >> 8) | ((unsigned long long)d << top);
   }
-  __device__ __forceinline__ void shift_down(int places) {  // 0 <= places <= LP
-#pragma unroll 1
-    for (int i = 0; i < places; i++) push_back(0u);
-  }
   __device__ __forceinline__ uint32_t get(int e) const {
     const unsigned long long v = (NW == 2 && e >= 8) ? w[NW - 1] : w[0];
     return (uint32_t)(v >> (8 * (e & 7))) & 0xffu;
@@ -330,8 +354,12 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
   // ---- stage B ----
   if constexpr (NL == 8) {
     float h[8];
+    float w[8];  // transition scores of the seven predecessor lists, in registers while stage B runs
 #pragma unroll
-    for (int i = 0; i < 8; i++) h[i] = i == V.s ? NEG : lds_f32(V.srcg + (uint32_t)i * TLS) + lds_f32(V.wrow + 4u * (uint32_t)i);
+    for (int i = 0; i < 8; i++) {
+      w[i] = lds_f32(V.wrow + 4u * (uint32_t)i);
+      h[i] = i == V.s ? NEG : lds_f32(V.srcg + (uint32_t)i * TLS) + w[i];
+    }
     float best, last_m = __int_as_float(0x7f800000);  // +inf: never equals a metric
     int i, last_i = -1;
     select_head<8>(h, best, i);
@@ -339,25 +367,26 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
     nB = 0;
     int e = 0;
 #pragma unroll 1
-    for (; e < LP; e++) {
+    for (; e < LP; e++) {  // always LP trips (no vote for an early exit: lists are full almost everywhere); a lane out of
+                           // candidates pushes descriptors of slots that exist and counts nothing
       const bool live = best != NEG;
-      if (!__any_sync(am, live)) break;
       const int j = (ptrs >> (4 * i)) & 15;
       desc.push_back((uint32_t)((i << 4) | j));
       nB += live ? 1 : 0;
       tie = tie || (live && best == last_m && i != last_i);
       last_m = best;
       last_i = i;
-      float nh = NEG;
+      // the popped list's next head: its raw metric (-inf when the list is exhausted: -inf + score = -inf) is added
+      // to the list's own score inside the conditional move, one predicated FADD per list
+      float raw = NEG;
       if (live && j + 1 < LP) {
-        nh = lds_f32(V.srcg + (uint32_t)i * TLS + (uint32_t)(j + 1) * TSS) + lds_f32(V.wrow + 4u * (uint32_t)i);
+        raw = lds_f32(V.srcg + (uint32_t)i * TLS + (uint32_t)(j + 1) * TSS);
         ptrs += 1u << (4 * i);
       }
 #pragma unroll
-      for (int i2 = 0; i2 < 8; i2++) h[i2] = (i2 == i) ? nh : h[i2];
+      for (int i2 = 0; i2 < 8; i2++) cond_add_if_eq(h[i2], i, i2, raw, w[i2]);
       select_head<8>(h, best, i);
     }
-    desc.shift_down(LP - e);
     tie = tie || (best != NEG && best == last_m);  // the candidate behind the LP-th: which of the two is in B?
   } else {
     const unsigned long long crfs = 0x1010101010101010ull * (unsigned long long)(uint32_t)(V.s - 4);
@@ -397,14 +426,11 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
     const uint32_t addr = V.mine + (uint32_t)a * SS;
     const float mA = lds_f32(addr) + wA;
     const uint32_t idA = lds_u32(addr + LS), ptA = lds_u32(addr + 2 * LS);
-    float tm = NEG;
-    uint32_t tb = 0;
+    uint32_t tb = 0, tmb = __float_as_uint(NEG);  // the twin among the move-in candidates (at most one): its bit and metric
+    const uint32_t one = lds_volatile_u32(V.one_addr);
 #pragma unroll
-    for (int e = 0; e < LP; e++) {
-      const bool eq = ((idA ^ idB[e]) | (ptA ^ ptB[e])) == 0u;
-      tm = eq ? mB[e] : tm;
-      tb = eq ? (1u << e) : tb;
-    }
+    for (int e = 0; e < LP; e++) cond_move2_if_pair_eq(tmb, tb, idA, idB[e], ptA, ptB[e], __float_as_uint(mB[e]), 1u << e, one);
+    const float tm = __uint_as_float(tmb);
     const bool has = tb != 0u && tm != NEG && mA != NEG;
     tie = tie || (has && mA == tm);
     if (has) {
@@ -418,23 +444,21 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
   uint32_t keepA = ~dropA & FULL, keepB = ~dropB & FULL;
   uint32_t addrA = V.mine, addrB = V.srcg, jA = 0, dB = 0;
   float hA = NEG, hB = NEG;
+  // heads without a branch: an empty side reads a slot that exists (its last one; descriptor 0 behind the live
+  // move-in candidates) and the value is replaced by -inf
   auto head_a = [&]() {
-    hA = NEG;
-    if (keepA != 0u) {
-      jA = (uint32_t)__ffs((int)keepA) - 1u;
-      addrA = V.mine + jA * SS;
-      hA = lds_f32(addrA) + wA;
-    }
+    jA = ((uint32_t)__ffs((int)keepA) - 1u) & (uint32_t)(LP - 1);
+    addrA = V.mine + jA * SS;
+    const float m = lds_f32(addrA) + wA;
+    hA = keepA != 0u ? m : NEG;
   };
   auto head_b = [&]() {
-    hB = NEG;
     const int eB = __ffs((int)keepB) - 1;
-    if (keepB != 0u && eB < nB) {
-      dB = desc.get(eB);
-      const uint32_t crf = dB >> 4;
-      addrB = V.srcg + crf * TLS + (dB & 15u) * TSS;
-      hB = lds_f32(addrB) + lds_f32(V.wrow + 4u * crf);
-    }
+    dB = desc.get(eB & (LP - 1));
+    const uint32_t crf = dB >> 4;
+    addrB = V.srcg + crf * TLS + (dB & 15u) * TSS;
+    const float m = lds_f32(addrB) + lds_f32(V.wrow + 4u * crf);
+    hB = (keepB != 0u && eB < nB) ? m : NEG;
   };
   head_a();
   head_b();
@@ -458,14 +482,15 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
     if (want_log) log.push(0u, pop_a ? ((own_list << 4) | jA) : (NL == 8 ? dB : (0x10u | (dB & 15u))));  // boundary rows: publish_ids()
     l++;
     last = best;
-    if (pop_a) {
-      keepA &= keepA - 1u;
-      head_a();
-    } else {
-      keepB &= keepB - 1u;
-      head_b();
-    }
-    if (l == LP) break;
+    // no divergent branch: only the popped side loses its head, and re-deriving the head of the other side gives the
+    // value it already has, so both are derived on every trip (a warp whose lanes pop from different sides ran both
+    // branches one after the other anyway)
+    const uint32_t popped = pop_a ? keepA : keepB, rest = popped & (popped - 1u);
+    keepA = pop_a ? rest : keepA;
+    keepB = pop_a ? keepB : rest;
+    head_a();
+    head_b();
+    if (l == LP) break;  // after the heads: the candidate behind the last one kept is tested for a tie below
   }
   tie = tie || (fmaxf(hA, hB) == last);  // the candidate behind the last one kept (l == 0: last = +inf)
   return tie ? -1 : l;
@@ -565,6 +590,7 @@ __global__ void __launch_bounds__(kFastThreads, LP <= 8 ? 4 : 2) lva_step_fast(c
     mbar_init(bar + 1, 1);
     mbar_init(bar + 2, 1);
     fence_barrier_init();
+    smem[kOneWord] = A.one;
   }
   if (!__syncthreads_or(valid)) return;
 
@@ -666,12 +692,12 @@ __global__ void __launch_bounds__(kFastThreads, LP <= 8 ? 4 : 2) lva_step_fast(c
     tab = A.tab + (unsigned long long)z * ((unsigned long long)A.tab_mask + 1ull);
   }
   if (role == 0) {
-    ListView<LP, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
+    ListView<LP, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s, smem_u32(smem + kOneWord)};
     V.pin();
     n_acc = merge_state<LP, 8>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar, R.boundary != 0);
     if (R.boundary && n_acc > 0) publish_ids<LP, 8>(V, log, n_acc, nidw, nid_own, tab, A, z);
   } else {
-    ListView<LP, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s};
+    ListView<LP, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s, smem_u32(smem + kOneWord)};
     V.pin();
     n_acc = merge_state<LP, 2>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar, R.boundary != 0);
     if (R.boundary && n_acc > 0) publish_ids<LP, 2>(V, log, n_acc, nidw, nid_own, tab, A, z);
