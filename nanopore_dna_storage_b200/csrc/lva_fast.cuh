@@ -339,7 +339,7 @@ struct DescVec {
 // to exact_merge() as before: a superset of the cases where libstdc++'s heap order could show.
 // Returns the number of accepted entries, or -1 on a tie.
 template <int LP, int NL>
-__device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP, NL> &V, AcceptLog<LP> &log, unsigned am,
+__device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP, NL> &V, AcceptLog<LP> &log,
                                                bool check, unsigned long long *counters, uint64_t *own_bar, bool want_log) {
   static_assert(LP <= 16, "stage T keeps 3*LP words of move-in candidates in registers (16 slots: 2 CTAs per SM by shared memory anyway)");
   using View = ListView<LP, NL>;
@@ -499,10 +499,10 @@ __device__ __forceinline__ int merge_two_stage(uint32_t *dst, const ListView<LP,
 // Which merge serves this state: rows without history, the two-stage merge, or the pop-by-pop loop.
 template <int LP, int NL>
 __device__ __forceinline__ int merge_state(uint32_t *dst, const ListView<LP, NL> &V, int L, AcceptLog<LP> &log, bool nohist,
-                                           bool two_stage, bool check, unsigned am,
+                                           bool two_stage, bool check,
                                            unsigned long long *counters, uint64_t *own_bar, bool want_log) {
   if constexpr (LP <= 16) {
-    if (two_stage && !nohist) return merge_two_stage<LP, NL>(dst, V, log, am, check, counters, own_bar, want_log);
+    if (two_stage && !nohist) return merge_two_stage<LP, NL>(dst, V, log, check, counters, own_bar, want_log);
   }
   mbar_wait(own_bar, 0);  // every other merge reads the own list from its first instruction on
   if (nohist) return merge_first_only<LP, NL>(dst, V, log);
@@ -675,7 +675,6 @@ __global__ void __launch_bounds__(kFastThreads, LP <= 8 ? 4 : 2) lva_step_fast(c
     return;
   }
   const int L = (int)K.L;
-  const unsigned am = __activemask();  // the lanes of this warp that own a valid state (roles are per warp)
   const bool two_stage = LP <= 16 && L == LP && !R.xdup && !(A.dbg & 4u);  // LVA_DBG bit 2: the pop-by-pop merge of merge_lists() everywhere
   const int row = s >= 4 ? 4 : s;
   const float *wrow = post + row * 8;
@@ -694,12 +693,12 @@ __global__ void __launch_bounds__(kFastThreads, LP <= 8 ? 4 : 2) lva_step_fast(c
   if (role == 0) {
     ListView<LP, 8> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s, smem_u32(smem + kOneWord)};
     V.pin();
-    n_acc = merge_state<LP, 8>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar, R.boundary != 0);
+    n_acc = merge_state<LP, 8>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, A.counters, own_bar, R.boundary != 0);
     if (R.boundary && n_acc > 0) publish_ids<LP, 8>(V, log, n_acc, nidw, nid_own, tab, A, z);
   } else {
     ListView<LP, 2> V{smem_u32(srcg), smem_u32(mine), smem_u32(wrow), keep, appv, s, smem_u32(smem + kOneWord)};
     V.pin();
-    n_acc = merge_state<LP, 2>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, am, A.counters, own_bar, R.boundary != 0);
+    n_acc = merge_state<LP, 2>(dst, V, L, log, R.nohist, two_stage, (A.dbg & 8u) != 0u, A.counters, own_bar, R.boundary != 0);
     if (R.boundary && n_acc > 0) publish_ids<LP, 2>(V, log, n_acc, nidw, nid_own, tab, A, z);
   }
   if (n_acc < 0) {  // metrics tie where libstdc++'s heap order could show: redo this state exactly
